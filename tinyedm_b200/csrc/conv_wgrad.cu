@@ -1,0 +1,248 @@
+// Weight gradient of the MPConv implicit GEMM on tcgen05/TMEM (sm_100a).
+//
+// autograd of F.conv2d w.r.t. its weight (reference: src/tinyedm/networks.py:37, no custom backward in
+// the reference) restated as a GEMM whose contraction runs over PIXELS:
+//     dW[co][tap][ci] = alpha * sum_p G[p][co] * X[p + off(tap)][ci]
+// Both operands are NHWC bf16, i.e. the contraction index (pixel) is the slow one: they are fed to the
+// tensor core as MN-major tiles (TMA box = rows of 64 channels, 128B swizzle; UMMA descriptors with
+// LBO = distance between 64-channel boxes, SBO = 1024 B between 8-pixel groups).
+// The zero padding of the shifted X tile comes from TMA out-of-bounds fill, the G tile uses the same
+// 4-D box so both operands hold exactly the same pixel set (rows beyond the image are zero in both).
+//
+// Work item = (co block of 128, tap, ci block of <=256, K split). Accumulator 128 x 256 fp32 in TMEM.
+// Split-K partial results are combined with fp32 vector atomics into a zeroed dW.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace tedm {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kBM = 128;      // Cout rows per CTA
+constexpr int kBN = 256;      // Cin columns per CTA (per tap)
+constexpr int kMaxRows = 64;  // pixels per pipeline stage
+constexpr int kStages = 4;
+constexpr int kBoxBytesMax = kMaxRows * 128;
+constexpr int kStageBytes = (kBM / 64 + kBN / 64) * kBoxBytesMax;  // 6 boxes = 48 KB
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+
+struct WgradParams {
+  int B, H, W, Cin, Cout, taps;
+  int RH, NB, rows;        // pixel tile = NB images x RH rows x W cols; rows % 16 == 0, rows <= 64
+  int tiles_h, p_tiles;    // pixel tiles
+  int co_blks, ci_blks, items, splits, tiles_per_split;
+  float alpha;
+  int use_atomics;
+  float* dw;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
+                  const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* acc_full = bars + 2 * kStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // work item decode
+  const int item = blockIdx.x % p.items;
+  const int split = blockIdx.x / p.items;
+  const int ci_blk = item % p.ci_blks;
+  const int tap = (item / p.ci_blks) % p.taps;
+  const int co_blk = item / (p.ci_blks * p.taps);
+  const int co0 = co_blk * kBM;
+  const int ci0 = ci_blk * kBN;
+  int n_this = p.Cin - ci0;
+  if (n_this > kBN) n_this = kBN;
+  const int n_boxes = n_this / 64;
+  const int dr = (p.taps == 9) ? tap / 3 - 1 : 0;
+  const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
+  const int t_begin = split * p.tiles_per_split;
+  int t_end = t_begin + p.tiles_per_split;
+  if (t_end > p.p_tiles) t_end = p.p_tiles;
+  const int box_bytes = p.rows * 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_g);
+    tma_prefetch_desc(&tmap_x);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, kBN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = (uint32_t)(2 + n_boxes) * box_bytes;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int bi = t / p.tiles_h;
+        const int b0 = bi * p.NB;
+        const int h0 = (t - bi * p.tiles_h) * p.RH;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* s = smem + stage * kStageBytes;
+        mbar_expect_tx(&full_bar[stage], tx);
+        tma_load_4d(s, &tmap_g, &full_bar[stage], co0, 0, h0, b0);
+        tma_load_4d(s + box_bytes, &tmap_g, &full_bar[stage], co0 + 64, 0, h0, b0);
+        uint8_t* xs = s + 2 * kBoxBytesMax;
+        for (int j = 0; j < n_boxes; ++j)
+          tma_load_4d(xs + j * box_bytes, &tmap_x, &full_bar[stage], ci0 + j * 64, ds, h0 + dr, b0);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t idesc = make_idesc_bf16(kBM, n_this, 1, 1);
+      const int ksteps = p.rows / 16;
+      bool first = true;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+        const uint32_t b_addr = a_addr + 2 * kBoxBytesMax;
+        const uint64_t a_desc = make_smem_desc_sw128(a_addr, box_bytes, 1024);
+        const uint64_t b_desc = make_smem_desc_sw128(b_addr, box_bytes, 1024);
+        for (int k = 0; k < ksteps; ++k) {
+          // 16 pixels (K) = 16 rows of 128 B = 2048 B
+          umma_bf16(tmem_base, a_desc + (uint64_t)(k * 128), b_desc + (uint64_t)(k * 128), idesc,
+                    first ? 0u : 1u);
+          first = false;
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(acc_full);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    if (t_end > t_begin) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+      float* dst = p.dw + ((long long)co * p.taps + tap) * p.Cin + ci0;
+      for (int c0 = 0; c0 < n_this; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c0, r);
+        tmem_ld_wait();
+        if (co < p.Cout) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float4 v = make_float4(__uint_as_float(r[g * 4 + 0]) * p.alpha, __uint_as_float(r[g * 4 + 1]) * p.alpha,
+                                   __uint_as_float(r[g * 4 + 2]) * p.alpha, __uint_as_float(r[g * 4 + 3]) * p.alpha);
+            float4* d4 = reinterpret_cast<float4*>(dst + c0 + g * 4);
+            if (p.use_atomics) {
+              atomicAdd(d4, v);
+            } else {
+              *d4 = v;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kBN);
+  }
+}
+
+// Pixel-tile geometry for the contraction: rows = NB*RH*W must be a multiple of 16 and <= 64.
+int wgrad_geometry(int H, int W, int* RH, int* NB) {
+  int best = 0;
+  for (int rh = 1; rh <= H; ++rh) {
+    if (rh * W > kMaxRows) break;
+    int nb_max = kMaxRows / (rh * W);
+    for (int nb = 1; nb <= nb_max; ++nb) {
+      int rows = rh * W * nb;
+      if (rows % 16 != 0) continue;
+      // prefer more rows; among equal, prefer fewer images per box (better halo reuse)
+      if (rows > best) { best = rows; *RH = rh; *NB = nb; }
+    }
+  }
+  return best > 0 ? 0 : -1;
+}
+
+}  // namespace
+
+int conv_wgrad_launch(const ConvWgradArgs& a, cudaStream_t stream) {
+  TEDM_CHECK(a.ksize == 1 || a.ksize == 3, "conv_wgrad: kernel size must be 1 or 3 (got %d)", a.ksize);
+  TEDM_CHECK(a.Cin % 64 == 0 && a.Cout % 64 == 0, "conv_wgrad: Cin/Cout must be multiples of 64 (got %d/%d)",
+             a.Cin, a.Cout);
+  TEDM_CHECK(a.B > 0 && a.H > 0 && a.W > 0, "conv_wgrad: empty input");
+  WgradParams p{};
+  p.B = a.B; p.H = a.H; p.W = a.W; p.Cin = a.Cin; p.Cout = a.Cout; p.taps = a.ksize * a.ksize;
+  TEDM_CHECK(wgrad_geometry(a.H, a.W, &p.RH, &p.NB) == 0, "conv_wgrad: unsupported spatial size %dx%d", a.H, a.W);
+  p.rows = p.RH * p.NB * a.W;
+  p.tiles_h = (a.H + p.RH - 1) / p.RH;
+  p.p_tiles = ((a.B + p.NB - 1) / p.NB) * p.tiles_h;
+  p.co_blks = (a.Cout + kBM - 1) / kBM;
+  p.ci_blks = (a.Cin + kBN - 1) / kBN;
+  p.items = p.co_blks * p.ci_blks * p.taps;
+  int splits = a.splits_override;
+  if (splits <= 0) {
+    int target = 2 * num_sms();
+    splits = (target + p.items - 1) / p.items;
+  }
+  if (splits > p.p_tiles) splits = p.p_tiles;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = (p.p_tiles + splits - 1) / splits;
+  splits = (p.p_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.splits = splits;
+  p.alpha = a.alpha;
+  p.use_atomics = (splits > 1 || a.accumulate) ? 1 : 0;
+  p.dw = a.dw;
+  if (splits > 1 && !a.accumulate)
+    TEDM_CUDA(cudaMemsetAsync(a.dw, 0, sizeof(float) * (size_t)a.Cout * p.taps * a.Cin, stream));
+
+  CUtensorMap tg, tx;
+  {
+    uint64_t dims[4] = {(uint64_t)a.Cout, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
+    uint64_t strides[3] = {(uint64_t)a.Cout * 2, (uint64_t)a.W * a.Cout * 2, (uint64_t)a.H * a.W * a.Cout * 2};
+    uint32_t box[4] = {64, (uint32_t)a.W, (uint32_t)p.RH, (uint32_t)p.NB};
+    if (encode_tmap(&tg, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.g, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) != 0)
+      return -1;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
+    uint64_t strides[3] = {(uint64_t)a.Cin * 2, (uint64_t)a.W * a.Cin * 2, (uint64_t)a.H * a.W * a.Cin * 2};
+    uint32_t box[4] = {64, (uint32_t)a.W, (uint32_t)p.RH, (uint32_t)p.NB};
+    if (encode_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) != 0)
+      return -1;
+  }
+  static bool configured = false;
+  if (!configured) {
+    TEDM_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    configured = true;
+  }
+  conv_wgrad_kernel<<<p.items * splits, kThreads, kSmemBytes, stream>>>(tg, tx, p);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tedm
