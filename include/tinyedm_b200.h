@@ -26,17 +26,110 @@ const char* tedm_last_error(void);
 /* Binds the calling thread to `device` and checks it is an sm_100 part. */
 int tedm_init(int device);
 
+/* ---- forced weight normalisation, all weight tensors in one launch (networks.py:17-19, :32-36, :55-59) ---- */
+typedef struct tedm_weight_desc {
+  void* w;           /* fp32 parameter, [rows][cin*taps] (OIHW flattened)                      */
+  void* grad;        /* fp32 dL/dw, same layout (written by tedm_weight_prep_backward)         */
+  const void* g_hat; /* fp32 dL/dw_hat, [rows][kpad] with k = tap*cin + ci                     */
+  void* out_fwd;     /* bf16 w_hat [rows][kpad], k = tap*cin + ci (zero padded)   or NULL      */
+  void* out_dgrad;   /* bf16 w_hat [cin][taps flipped][rows]                      or NULL      */
+  void* out_f32;     /* fp32 w_hat [rows][cin*taps]                               or NULL      */
+  void* stats;       /* fp32 [rows][2] = {1/(eps*sqrt(n)+||w||), ||w||}                        */
+  int32_t rows, cin, taps, kpad, row_start, reserved[3];
+} tedm_weight_desc;
+/* table: DEVICE array of n descriptors ordered by row_start; total_rows = sum(rows).
+ * training != 0 additionally rewrites every parameter in place: w <- normalize(w)  (networks.py:32-34). */
+int tedm_weight_prep_forward(const tedm_weight_desc* table, int n, int total_rows, int training, tedm_stream_t stream);
+/* dL/dw = g/s - w (w.g)/(s^2 ||w||) for every descriptor with g_hat and grad set (autograd of :35-36). */
+int tedm_weight_prep_backward(const tedm_weight_desc* table, int n, int total_rows, tedm_stream_t stream);
+
 /* ---- MPConv: F.conv2d(x, w_hat, padding="same")  (networks.py:22-43, :37) ---- */
-/* epilogue: 0 plain (out = alpha*conv)
- *           1 modulation + mp_silu + dropout: out = drop(mp_silu(conv * mod[b,c]))   (networks.py:255-260, :319-324)
+/* The same entry computes the data gradient: pass g as x and the out_dgrad weight layout (Cin/Cout swapped).
+ * epilogue: 0 plain (out = alpha*conv)
+ *           1 modulation + mp_silu + dropout: out = drop(mp_silu(alpha*conv * mod[b,c]))  (networks.py:255-260, :319-324)
  *             raw (optional) receives the un-modulated conv output for backward
- *           2 mp_add: out = ((1-t)*res + t*conv) / sqrt((1-t)^2+t^2)                  (networks.py:87-88, :263, :327) */
+ *           2 axpby: out = alpha*conv + beta*res; mp_add(x, conv, t) is alpha = t/c, beta = (1-t)/c,
+ *             c = sqrt((1-t)^2+t^2)                                                     (networks.py:87-88, :263, :327) */
 int tedm_conv2d_forward(const void* x, const void* w, void* out, int B, int H, int W, int Cin, int Cout, int ksize,
-                        int epilogue, float alpha, void* raw, const void* res, float t, const float* mod,
+                        int epilogue, float alpha, void* raw, const void* res, float beta, const float* mod,
                         int mod_stride, float drop_p, uint64_t seed, int block_n, tedm_stream_t stream);
 /* dL/dw_hat of the convolution above: dw[co][tap][ci] (=|+=) alpha * sum_p g[p,co] * x[p+tap,ci]  (autograd of :37) */
 int tedm_conv2d_wgrad(const void* g, const void* x, float* dw, int B, int H, int W, int Cin, int Cout, int ksize,
                       float alpha, int accumulate, int splits, tedm_stream_t stream);
+
+/* ---- bandwidth-bound block kernels (NHWC bf16) ---- */
+/* resample (0 none / 1 avg-pool 2x2 / 2 nearest-exact x2), skip concat with ScaleLong gain, pixel_norm, mp_silu in one
+ * pass: networks.py:9-14, :67-88, :246-252 (encoder), :306-316 (decoder). Any of x_out / a_out / nrm_out may be NULL. */
+int tedm_block_prep_forward(const void* in, const void* skip, const float* gain, void* x_out, void* a_out, float* nrm_out,
+                            int B, int Hin, int Win, int C1, int C2, int resample, int pixelnorm, tedm_stream_t stream);
+/* adjoint of the above: g_x = beta*g_res + g_a*mp_silu'(x), pixel_norm / resample / concat adjoints. */
+int tedm_block_prep_backward(const void* g_res, float beta, const void* g_a, const void* x, const float* nrm,
+                             const float* gain, const float* d_mean, void* g_in, void* g_skip, int accumulate_in,
+                             int accumulate_skip, int B, int Hin, int Win, int C1, int C2, int resample, int pixelnorm,
+                             tedm_stream_t stream);
+/* backward of dropout(mp_silu(raw * mod[b,c])) (networks.py:255-261): g_raw, and d_mod[b,c] += sum_hw (zero d_mod first). */
+int tedm_modsilu_backward(const void* g_h, const void* raw, const float* mod, float* d_mod, void* g_raw, int B, int HW,
+                          int C, int mod_stride, float drop_p, uint64_t seed, tedm_stream_t stream);
+/* out[b,c] += scale * sum_p A[b,p,a_off+c] * (Bm ? Bm[b,p,c] : 1)   (ScaleLong mean networks.py:115 and its adjoint) */
+int tedm_channel_dot(const void* A, const void* Bm, float* out, int B, int HW, int C, int CA, int a_off, float scale,
+                     tedm_stream_t stream);
+
+/* ---- cosine attention core (networks.py:194-202): qkv (B,S,3C) interleaved -> y (B,S,C) ---- */
+/* qkvn: workspace [3][B][heads][S][hd] bf16 (normalised q,k,v, kept for backward); lse: (B*heads*S) fp32 */
+int tedm_attention_forward(const void* qkv, void* qkvn, void* y, float* lse, int B, int S, int heads, int head_dim,
+                           tedm_stream_t stream);
+int tedm_attention_backward(const void* qkv, const void* qkvn, const void* y, const void* g_y, const float* lse,
+                            float* delta_ws, void* g_qkvn_ws, void* g_qkv, int B, int S, int heads, int head_dim,
+                            tedm_stream_t stream);
+
+/* ---- small fp32 layers ---- */
+/* C[M,N] = alpha*op(A)*op(B) + beta*C, row-major fp32 (F.linear of the autocast-off islands, networks.py:46-64) */
+int tedm_sgemm(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int transA,
+               int transB, float alpha, float beta, tedm_stream_t stream);
+/* Embedding.forward (networks.py:163-178): sigma (B,) or 0-d (sigma_stride 0), labels int64 (B,) or NULL */
+int tedm_embedding_forward(const float* sigma, int sigma_stride, const float* freqs, const float* phases,
+                           const float* w_sigma, const float* w_class, const int64_t* labels, float* fourier, float* pre,
+                           float* emb, int B, int F, int E, int n_classes, float add_factor, tedm_stream_t stream);
+int tedm_embedding_backward(const float* g_emb, const float* pre, const int64_t* labels, float* g_sig, float* g_w_class,
+                            int B, int E, int n_classes, float add_factor, tedm_stream_t stream);
+/* m[b,col] = lin[b,col]*gain[block(col)] + 1 for all blocks (networks.py:255-258): gains = device array of pointers */
+int tedm_mod_finish_forward(const float* lin, const void* gains, const int32_t* col_block, float* m, int B, int N,
+                            tedm_stream_t stream);
+int tedm_mod_finish_backward(const float* lin, const float* dm, const void* gains, const int32_t* blk_start, float* d_lin,
+                             float* d_gain, int B, int N, int n_blocks, tedm_stream_t stream);
+/* ScaleLong (networks.py:106-118) on the spatial mean: gain = sigmoid(W2 mp_silu(W1 [mean,1])) */
+int tedm_scalelong_forward(const float* mean, const float* w1, const float* w2, float* aug, float* h_pre, float* h,
+                           float* gain, int B, int C, int R, tedm_stream_t stream);
+int tedm_scalelong_backward(const float* d_gain, const float* gain, const float* h_pre, const float* w1, const float* w2,
+                            float* d_pre2, float* d_hpre, float* d_mean, int B, int C, int R, tedm_stream_t stream);
+/* UncertaintyNet (networks.py:91-103) */
+int tedm_uncertainty_forward(const float* fourier, const float* w1, const float* w2, const float* gain, float* aug,
+                             float* h_pre, float* h, float* u_raw, float* u, int B, int F, tedm_stream_t stream);
+int tedm_uncertainty_backward(const float* g_u, const float* gain, const float* w2, const float* h_pre, float* g_uraw,
+                              float* g_hpre, int B, int F, tedm_stream_t stream);
+
+/* ---- image-sized kernels ---- */
+/* c_in*x, ones channel, 3x3 patch gather -> (B,H,W,64) bf16 (networks.py:578-587) */
+int tedm_conv_in_im2col(const float* noisy, const float* sigma, int sigma_stride, float sigma_data, void* out, int B,
+                        int Ci, int H, int W, tedm_stream_t stream);
+/* D = conv_out(x)*gain_out*c_out + noisy*c_skip (networks.py:602-603); f_raw (optional) keeps conv_out(x) */
+int tedm_conv_out_forward(const void* x, const void* w, const float* gain_out, const float* noisy, const float* sigma,
+                          int sigma_stride, float sigma_data, float* f_raw, float* D, int B, int HW, int C, int Co,
+                          tedm_stream_t stream);
+int tedm_conv_out_backward(const float* g_D, const float* f_raw, const void* x, const void* w, const float* gain_out,
+                           const float* sigma, int sigma_stride, float sigma_data, void* g_x, float* g_w,
+                           float* g_gain_out, int B, int HW, int C, int Co, tedm_stream_t stream);
+/* loss = sum_b w_b * mean_chw((D-y)^2) / B [+ mean(u)], w_b = lambda(sigma_b) [* exp(-u_b)]  (edm.py:212-219, metric.py:8-18) */
+int tedm_wmse_forward(const float* D, const float* y, const float* sigma, const float* u, float sigma_data, float* mse,
+                      float* loss, int B, int n, tedm_stream_t stream);
+int tedm_wmse_backward(const float* D, const float* y, const float* sigma, const float* u, const float* mse,
+                       const float* g_loss, float sigma_data, float* g_D, float* g_u, int B, int n, tedm_stream_t stream);
+/* Heun stages (solvers.py:45-57): mode 0 Euler predictor, 1 trapezoid corrector, 2 x*t_0; ts = device schedule */
+int tedm_heun_step(const float* x0, const float* x1, const float* D, const float* d_prev, float* x_out, float* d_out,
+                   const float* ts, int step, int mode, int64_t n, tedm_stream_t stream);
+/* Diffuser.forward (edm.py:84-93) with the two normal draws supplied by the caller */
+int tedm_diffuse(const float* clean, const float* eps, const float* noise, float P_mean, float P_std, float* noisy,
+                 float* sigma, int B, int n, tedm_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,7 @@ int tedm_init(int device) {
 }
 
 int tedm_conv2d_forward(const void* x, const void* w, void* out, int B, int H, int W, int Cin, int Cout, int ksize,
-                        int epilogue, float alpha, void* raw, const void* res, float t, const float* mod,
+                        int epilogue, float alpha, void* raw, const void* res, float beta, const float* mod,
                         int mod_stride, float drop_p, uint64_t seed, int block_n, tedm_stream_t stream) {
   ConvGemmArgs a{};
   a.x = static_cast<const __nv_bfloat16*>(x);
@@ -32,8 +32,7 @@ int tedm_conv2d_forward(const void* x, const void* w, void* out, int B, int H, i
   a.epi = epilogue; a.alpha = alpha;
   a.out2 = static_cast<__nv_bfloat16*>(raw);
   a.res = static_cast<const __nv_bfloat16*>(res);
-  a.t = t;
-  a.inv_c = 1.0f / sqrtf((1.0f - t) * (1.0f - t) + t * t);
+  a.beta = beta;
   a.mod = mod; a.mod_stride = mod_stride; a.drop_p = drop_p; a.seed = seed;
   a.block_n_override = block_n;
   return conv_gemm_launch(a, static_cast<cudaStream_t>(stream));
@@ -48,6 +47,130 @@ int tedm_conv2d_wgrad(const void* g, const void* x, float* dw, int B, int H, int
   a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize;
   a.alpha = alpha; a.accumulate = accumulate; a.splits_override = splits;
   return conv_wgrad_launch(a, static_cast<cudaStream_t>(stream));
+}
+
+#define BF(p) static_cast<__nv_bfloat16*>(p)
+#define CBF(p) static_cast<const __nv_bfloat16*>(p)
+#define ST(s) static_cast<cudaStream_t>(s)
+
+int tedm_weight_prep_forward(const tedm_weight_desc* table, int n, int total_rows, int training, tedm_stream_t stream) {
+  return weight_prep_forward(table, n, total_rows, training, ST(stream));
+}
+int tedm_weight_prep_backward(const tedm_weight_desc* table, int n, int total_rows, tedm_stream_t stream) {
+  return weight_prep_backward(table, n, total_rows, ST(stream));
+}
+
+int tedm_block_prep_forward(const void* in, const void* skip, const float* gain, void* x_out, void* a_out, float* nrm_out,
+                            int B, int Hin, int Win, int C1, int C2, int resample, int pixelnorm, tedm_stream_t stream) {
+  PrepArgs a{CBF(in), CBF(skip), gain, BF(x_out), BF(a_out), nrm_out, B, Hin, Win, C1, C2, resample, pixelnorm};
+  return block_prep_forward(a, ST(stream));
+}
+int tedm_block_prep_backward(const void* g_res, float beta, const void* g_a, const void* x, const float* nrm,
+                             const float* gain, const float* d_mean, void* g_in, void* g_skip, int accumulate_in,
+                             int accumulate_skip, int B, int Hin, int Win, int C1, int C2, int resample, int pixelnorm,
+                             tedm_stream_t stream) {
+  PrepBwdArgs a{CBF(g_res), beta, CBF(g_a), CBF(x), nrm, gain, d_mean, BF(g_in), BF(g_skip), accumulate_in,
+                accumulate_skip, B, Hin, Win, C1, C2, resample, pixelnorm};
+  return block_prep_backward(a, ST(stream));
+}
+int tedm_modsilu_backward(const void* g_h, const void* raw, const float* mod, float* d_mod, void* g_raw, int B, int HW,
+                          int C, int mod_stride, float drop_p, uint64_t seed, tedm_stream_t stream) {
+  ModSiluBwdArgs a{CBF(g_h), CBF(raw), mod, d_mod, BF(g_raw), B, HW, C, mod_stride, drop_p, (uint32_t)seed,
+                   (uint32_t)(seed >> 32)};
+  return modsilu_backward(a, ST(stream));
+}
+int tedm_channel_dot(const void* A, const void* Bm, float* out, int B, int HW, int C, int CA, int a_off, float scale,
+                     tedm_stream_t stream) {
+  ChannelDotArgs a{CBF(A), CBF(Bm), out, B, HW, C, CA, a_off, scale};
+  return channel_dot(a, ST(stream));
+}
+int tedm_attention_forward(const void* qkv, void* qkvn, void* y, float* lse, int B, int S, int heads, int head_dim,
+                           tedm_stream_t stream) {
+  return attention_forward(CBF(qkv), BF(qkvn), BF(y), lse, B, S, heads, head_dim, ST(stream));
+}
+int tedm_attention_backward(const void* qkv, const void* qkvn, const void* y, const void* g_y, const float* lse,
+                            float* delta_ws, void* g_qkvn_ws, void* g_qkv, int B, int S, int heads, int head_dim,
+                            tedm_stream_t stream) {
+  return attention_backward(CBF(qkv), CBF(qkvn), CBF(y), CBF(g_y), lse, delta_ws, BF(g_qkvn_ws), BF(g_qkv), B, S, heads,
+                            head_dim, ST(stream));
+}
+int tedm_sgemm(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int transA,
+               int transB, float alpha, float beta, tedm_stream_t stream) {
+  return sgemm(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, alpha, beta, ST(stream));
+}
+int tedm_embedding_forward(const float* sigma, int sigma_stride, const float* freqs, const float* phases,
+                           const float* w_sigma, const float* w_class, const int64_t* labels, float* fourier, float* pre,
+                           float* emb, int B, int F, int E, int n_classes, float add_factor, tedm_stream_t stream) {
+  EmbeddingArgs a{sigma, sigma_stride, freqs, phases, w_sigma, w_class, reinterpret_cast<const long long*>(labels),
+                  fourier, pre, emb, B, F, E, n_classes, add_factor};
+  return embedding_forward(a, ST(stream));
+}
+int tedm_embedding_backward(const float* g_emb, const float* pre, const int64_t* labels, float* g_sig, float* g_w_class,
+                            int B, int E, int n_classes, float add_factor, tedm_stream_t stream) {
+  EmbeddingBwdArgs a{g_emb, pre, reinterpret_cast<const long long*>(labels), g_sig, g_w_class, B, E, n_classes, add_factor};
+  return embedding_backward(a, ST(stream));
+}
+int tedm_mod_finish_forward(const float* lin, const void* gains, const int32_t* col_block, float* m, int B, int N,
+                            tedm_stream_t stream) {
+  return mod_finish_forward(lin, static_cast<const float* const*>(gains), col_block, m, B, N, ST(stream));
+}
+int tedm_mod_finish_backward(const float* lin, const float* dm, const void* gains, const int32_t* blk_start, float* d_lin,
+                             float* d_gain, int B, int N, int n_blocks, tedm_stream_t stream) {
+  return mod_finish_backward(lin, dm, static_cast<const float* const*>(gains), blk_start, d_lin, d_gain, B, N, n_blocks,
+                             ST(stream));
+}
+int tedm_scalelong_forward(const float* mean, const float* w1, const float* w2, float* aug, float* h_pre, float* h,
+                           float* gain, int B, int C, int R, tedm_stream_t stream) {
+  ScaleLongArgs a{mean, w1, w2, aug, h_pre, h, gain, B, C, R};
+  return scalelong_forward(a, ST(stream));
+}
+int tedm_scalelong_backward(const float* d_gain, const float* gain, const float* h_pre, const float* w1, const float* w2,
+                            float* d_pre2, float* d_hpre, float* d_mean, int B, int C, int R, tedm_stream_t stream) {
+  ScaleLongBwdArgs a{d_gain, gain, h_pre, w1, w2, d_pre2, d_hpre, d_mean, B, C, R};
+  return scalelong_backward(a, ST(stream));
+}
+int tedm_uncertainty_forward(const float* fourier, const float* w1, const float* w2, const float* gain, float* aug,
+                             float* h_pre, float* h, float* u_raw, float* u, int B, int F, tedm_stream_t stream) {
+  UncertaintyArgs a{fourier, w1, w2, gain, aug, h_pre, h, u_raw, u, B, F};
+  return uncertainty_forward(a, ST(stream));
+}
+int tedm_uncertainty_backward(const float* g_u, const float* gain, const float* w2, const float* h_pre, float* g_uraw,
+                              float* g_hpre, int B, int F, tedm_stream_t stream) {
+  UncertaintyBwdArgs a{g_u, gain, w2, h_pre, g_uraw, g_hpre, B, F};
+  return uncertainty_backward(a, ST(stream));
+}
+int tedm_conv_in_im2col(const float* noisy, const float* sigma, int sigma_stride, float sigma_data, void* out, int B,
+                        int Ci, int H, int W, tedm_stream_t stream) {
+  return conv_in_im2col(noisy, sigma, sigma_stride, sigma_data, BF(out), B, Ci, H, W, ST(stream));
+}
+int tedm_conv_out_forward(const void* x, const void* w, const float* gain_out, const float* noisy, const float* sigma,
+                          int sigma_stride, float sigma_data, float* f_raw, float* D, int B, int HW, int C, int Co,
+                          tedm_stream_t stream) {
+  ConvOutArgs a{CBF(x), CBF(w), gain_out, noisy, sigma, sigma_stride, sigma_data, f_raw, D, B, HW, C, Co};
+  return conv_out_forward(a, ST(stream));
+}
+int tedm_conv_out_backward(const float* g_D, const float* f_raw, const void* x, const void* w, const float* gain_out,
+                           const float* sigma, int sigma_stride, float sigma_data, void* g_x, float* g_w,
+                           float* g_gain_out, int B, int HW, int C, int Co, tedm_stream_t stream) {
+  ConvOutBwdArgs a{g_D, f_raw, CBF(x), CBF(w), gain_out, sigma, sigma_stride, sigma_data, BF(g_x), g_w, g_gain_out,
+                   B, HW, C, Co};
+  return conv_out_backward(a, ST(stream));
+}
+int tedm_wmse_forward(const float* D, const float* y, const float* sigma, const float* u, float sigma_data, float* mse,
+                      float* loss, int B, int n, tedm_stream_t stream) {
+  return wmse_forward(D, y, sigma, u, sigma_data, mse, loss, B, n, ST(stream));
+}
+int tedm_wmse_backward(const float* D, const float* y, const float* sigma, const float* u, const float* mse,
+                       const float* g_loss, float sigma_data, float* g_D, float* g_u, int B, int n, tedm_stream_t stream) {
+  return wmse_backward(D, y, sigma, u, mse, g_loss, sigma_data, g_D, g_u, B, n, ST(stream));
+}
+int tedm_heun_step(const float* x0, const float* x1, const float* D, const float* d_prev, float* x_out, float* d_out,
+                   const float* ts, int step, int mode, int64_t n, tedm_stream_t stream) {
+  return heun_step(x0, x1, D, d_prev, x_out, d_out, ts, step, mode, (long long)n, ST(stream));
+}
+int tedm_diffuse(const float* clean, const float* eps, const float* noise, float P_mean, float P_std, float* noisy,
+                 float* sigma, int B, int n, tedm_stream_t stream) {
+  return diffuse(clean, eps, noise, P_mean, P_std, noisy, sigma, B, n, ST(stream));
 }
 
 }  // extern "C"

@@ -232,9 +232,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 v[g * 4 + 3] = rnd.w >= thresh ? v[g * 4 + 3] * keep_scale : 0.f;
               }
             }
-          } else if (p.epi == EPI_MPADD) {
+          } else if (p.epi == EPI_AXPBY) {
             const __nv_bfloat16* res_row = p.res + pix * p.Cout + t.n0 + c0;
-            const float wa = (1.0f - p.t) * p.inv_c, wb = p.t * p.inv_c;
+            const float wa = p.beta, wb = 1.0f;  // alpha already applied to v[]
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               if (c0 + g * 8 < n_this) {
@@ -333,10 +333,10 @@ int conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t stream) {
   p.n_tiles = (a.Cout + bn - 1) / bn;
   p.k_blocks = p.taps * (a.Cin / 64);
   p.epi = a.epi; p.alpha = a.alpha; p.out = a.out; p.out2 = a.out2; p.res = a.res;
-  p.t = a.t; p.inv_c = a.inv_c; p.mod = a.mod; p.mod_stride = a.mod_stride;
+  p.beta = a.beta; p.mod = a.mod; p.mod_stride = a.mod_stride;
   p.drop_p = a.drop_p; p.seed_lo = (uint32_t)a.seed; p.seed_hi = (uint32_t)(a.seed >> 32);
   if (a.epi == EPI_MODSILU) TEDM_CHECK(a.mod != nullptr, "conv_gemm: MODSILU epilogue needs mod");
-  if (a.epi == EPI_MPADD) TEDM_CHECK(a.res != nullptr, "conv_gemm: MPADD epilogue needs res");
+  if (a.epi == EPI_AXPBY) TEDM_CHECK(a.res != nullptr, "conv_gemm: AXPBY epilogue needs res");
 
   CUtensorMap ta, tb;
   {

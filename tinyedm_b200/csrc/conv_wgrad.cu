@@ -21,15 +21,16 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kBM = 128;      // Cout rows per CTA
 constexpr int kBN = 256;      // Cin columns per CTA (per tap)
-constexpr int kMaxRows = 64;  // pixels per pipeline stage
-constexpr int kStages = 4;
-constexpr int kBoxBytesMax = kMaxRows * 128;
-constexpr int kStageBytes = (kBM / 64 + kBN / 64) * kBoxBytesMax;  // 6 boxes = 48 KB
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+constexpr int kPrefRows = 64;  // preferred pixels per pipeline stage (4 stages of 48 KB)
+constexpr int kMaxRows = 128;  // fallback for widths where no <=64-row tile is a multiple of 16 (2 stages)
+constexpr int kMaxStages = 4;
+constexpr int kTileBytes = 4 * (kBM / 64 + kBN / 64) * kPrefRows * 128;  // 192 KB of operand stages
+constexpr int kSmemBytes = kTileBytes + 1024 /*align*/ + 1024 /*barriers*/;
 
 struct WgradParams {
   int B, H, W, Cin, Cout, taps;
-  int RH, NB, rows;        // pixel tile = NB images x RH rows x W cols; rows % 16 == 0, rows <= 64
+  int RH, NB, rows;        // pixel tile = NB images x RH rows x W cols; rows % 16 == 0, rows <= 128
+  int stages, stage_bytes; // pipeline depth and bytes per stage (6 boxes of rows*128 B)
   int tiles_h, p_tiles;    // pixel tiles
   int co_blks, ci_blks, items, splits, tiles_per_split;
   float alpha;
@@ -42,11 +43,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
                   const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + kStages;
-  uint64_t* acc_full = bars + 2 * kStages;
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* acc_full = bars + 2 * kMaxStages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+  smem += 1024;
+  const int kStages = p.stages;
+  const int kStageBytes = p.stage_bytes;
+  const int kBoxBytesMax = p.rows * 128;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -173,7 +178,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
 }
 
 // Pixel-tile geometry for the contraction: rows = NB*RH*W must be a multiple of 16 and <= 64.
-int wgrad_geometry(int H, int W, int* RH, int* NB) {
+int wgrad_geometry_rows(int H, int W, int max_rows, int* RH, int* NB) {
   int best = 0;
   for (int rh = 1; rh <= H; ++rh) {
     if (rh * W > kMaxRows) break;
@@ -185,7 +190,12 @@ int wgrad_geometry(int H, int W, int* RH, int* NB) {
       if (rows > best) { best = rows; *RH = rh; *NB = nb; }
     }
   }
-  return best > 0 ? 0 : -1;
+  return best;
+}
+
+int wgrad_geometry(int H, int W, int* RH, int* NB) {
+  if (wgrad_geometry_rows(H, W, kPrefRows, RH, NB) > 0) return 0;
+  return wgrad_geometry_rows(H, W, kMaxRows, RH, NB) > 0 ? 0 : -1;
 }
 
 }  // namespace
@@ -199,6 +209,10 @@ int conv_wgrad_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   p.B = a.B; p.H = a.H; p.W = a.W; p.Cin = a.Cin; p.Cout = a.Cout; p.taps = a.ksize * a.ksize;
   TEDM_CHECK(wgrad_geometry(a.H, a.W, &p.RH, &p.NB) == 0, "conv_wgrad: unsupported spatial size %dx%d", a.H, a.W);
   p.rows = p.RH * p.NB * a.W;
+  p.stage_bytes = (kBM / 64 + kBN / 64) * p.rows * 128;
+  p.stages = kTileBytes / p.stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  TEDM_CHECK(p.stages >= 2, "conv_wgrad: pixel tile of %d rows does not fit two pipeline stages", p.rows);
   p.tiles_h = (a.H + p.RH - 1) / p.RH;
   p.p_tiles = ((a.B + p.NB - 1) / p.NB) * p.tiles_h;
   p.co_blks = (a.Cout + kBM - 1) / kBM;

@@ -6,12 +6,18 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/tinyedm_b200.h"
+
 namespace tedm {
+
+typedef tedm_weight_desc WeightDesc;
+int weight_prep_forward(const WeightDesc* table_dev, int n_tensors, int total_rows, int training, cudaStream_t stream);
+int weight_prep_backward(const WeightDesc* table_dev, int n_tensors, int total_rows, cudaStream_t stream);
 
 enum ConvEpilogue : int {
   EPI_PLAIN = 0,    // out = alpha * acc
   EPI_MODSILU = 1,  // out = dropout(mp_silu(acc * mod[b, c])); optional raw copy of acc in out2
-  EPI_MPADD = 2,    // out = ((1 - t) * res + t * acc) * inv_c            (mp_add, networks.py:87-88)
+  EPI_AXPBY = 2,    // out = alpha * acc + beta * res   (mp_add, networks.py:87-88: alpha = t/c, beta = (1-t)/c)
 };
 
 struct ConvGemmArgs {
@@ -22,8 +28,8 @@ struct ConvGemmArgs {
   int epi;
   float alpha;
   __nv_bfloat16* out2;       // MODSILU: raw conv output (may be null)
-  const __nv_bfloat16* res;  // MPADD: residual (B,H,W,Cout)
-  float t, inv_c;
+  const __nv_bfloat16* res;  // AXPBY: residual (B,H,W,Cout)
+  float beta;
   const float* mod;          // MODSILU: (B, mod_stride) fp32, column offset already applied
   int mod_stride;
   float drop_p;
@@ -40,7 +46,7 @@ struct ConvGemmParams {
   __nv_bfloat16* out;
   __nv_bfloat16* out2;
   const __nv_bfloat16* res;
-  float t, inv_c;
+  float beta;
   const float* mod;
   int mod_stride;
   float drop_p;
@@ -60,5 +66,155 @@ struct ConvWgradArgs {
   int splits_override;     // 0 = heuristic
 };
 int conv_wgrad_launch(const ConvWgradArgs& a, cudaStream_t stream);
+
+// ---- elementwise.cu ----
+struct PrepArgs {
+  const __nv_bfloat16* in;    // (B,Hin,Win,C1)
+  const __nv_bfloat16* skip;  // (B,Hin,Win,C2) or null
+  const float* gain;          // (B,C2) ScaleLong gain or null
+  __nv_bfloat16* x_out;       // (B,H,W,C1+C2) or null
+  __nv_bfloat16* a_out;       // mp_silu(x) or null
+  float* nrm_out;             // (B,H,W) eps + rms_C, written when pixelnorm (may be null)
+  int B, Hin, Win, C1, C2;
+  int resample;               // 0 none, 1 avg-pool 2x2, 2 nearest-exact x2
+  int pixelnorm;
+};
+int block_prep_forward(const PrepArgs& a, cudaStream_t stream);
+
+struct PrepBwdArgs {
+  const __nv_bfloat16* g_res;  // gradient reaching x through the residual path (scaled by beta) or null
+  float beta;
+  const __nv_bfloat16* g_a;    // gradient w.r.t. mp_silu(x) or null
+  const __nv_bfloat16* x;      // saved x (needed with g_a or pixelnorm)
+  const float* nrm;            // saved eps + rms (pixelnorm)
+  const float* gain;           // (B,C2) or null
+  const float* d_mean;         // (B,C2) gradient w.r.t. the spatial mean of skip (ScaleLong path) or null
+  __nv_bfloat16* g_in;         // (B,Hin,Win,C1)
+  __nv_bfloat16* g_skip;       // (B,Hin,Win,C2) or null
+  int accumulate_in, accumulate_skip;
+  int B, Hin, Win, C1, C2, resample, pixelnorm;
+};
+int block_prep_backward(const PrepBwdArgs& a, cudaStream_t stream);
+
+struct ModSiluBwdArgs {
+  const __nv_bfloat16* g_h;   // (B,HW,C)
+  const __nv_bfloat16* raw;   // (B,HW,C) un-modulated conv output
+  const float* mod;           // (B, mod_stride), column offset applied
+  float* d_mod;               // same indexing as mod; accumulated atomically (zero it first)
+  __nv_bfloat16* g_raw;       // (B,HW,C)
+  int B, HW, C, mod_stride;
+  float drop_p;
+  uint32_t seed_lo, seed_hi;
+};
+int modsilu_backward(const ModSiluBwdArgs& a, cudaStream_t stream);
+
+struct ChannelDotArgs {
+  const __nv_bfloat16* A;   // (B,HW,CA), columns [a_off, a_off + C) used
+  const __nv_bfloat16* Bm;  // (B,HW,C) or null (plain channel sum)
+  float* out;               // (B,C) accumulated atomically (zero it first)
+  int B, HW, C, CA, a_off;
+  float scale;
+};
+int channel_dot(const ChannelDotArgs& a, cudaStream_t stream);
+
+// ---- attention.cu ----
+int attention_forward(const __nv_bfloat16* qkv, __nv_bfloat16* qkvn, __nv_bfloat16* y, float* lse, int B, int S,
+                      int heads, int hd, cudaStream_t stream);
+int attention_backward(const __nv_bfloat16* qkv, const __nv_bfloat16* qkvn, const __nv_bfloat16* y,
+                       const __nv_bfloat16* g_y, const float* lse, float* delta, __nv_bfloat16* g_qkvn,
+                       __nv_bfloat16* g_qkv, int B, int S, int heads, int hd, cudaStream_t stream);
+
+// ---- small.cu ----
+int sgemm(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
+          float alpha, float beta, cudaStream_t stream);
+
+struct EmbeddingArgs {
+  const float* sigma; int sigma_stride;      // (B,) or 0-d (stride 0)
+  const float* freqs; const float* phases;   // (F,)
+  const float* w_sigma;                      // w_hat fp32 (E,F)
+  const float* w_class;                      // w_hat fp32 (E,n_classes) or null
+  const long long* labels;                   // (B,) int64 or null
+  float* fourier; float* pre; float* emb;    // (B,F), (B,E), (B,E)
+  int B, F, E, n_classes;
+  float add_factor;
+};
+int embedding_forward(const EmbeddingArgs& a, cudaStream_t stream);
+struct EmbeddingBwdArgs {
+  const float* g_emb; const float* pre; const long long* labels;
+  float* g_sig;        // (B,E): gradient w.r.t. sigma_embed output
+  float* g_w_class;    // (E,n_classes) accumulated atomically (zero first) or null
+  int B, E, n_classes;
+  float add_factor;
+};
+int embedding_backward(const EmbeddingBwdArgs& a, cudaStream_t stream);
+int mod_finish_forward(const float* lin, const float* const* gains, const int* col_block, float* m, int B, int N,
+                       cudaStream_t stream);
+int mod_finish_backward(const float* lin, const float* dm, const float* const* gains, const int* blk_start, float* d_lin,
+                        float* d_gain, int B, int N, int n_blocks, cudaStream_t stream);
+
+struct ScaleLongArgs {
+  const float* mean;   // (B,C) spatial mean of skip
+  const float* w1;     // w_hat fp32 (R, C+1)
+  const float* w2;     // w_hat fp32 (C, R)
+  float* aug_out;      // (B,C+1) = [mean, 1]
+  float* h_pre;        // (B,R)
+  float* h_out;        // (B,R) mp_silu(h_pre)
+  float* gain;         // (B,C)
+  int B, C, R;
+};
+int scalelong_forward(const ScaleLongArgs& a, cudaStream_t stream);
+struct ScaleLongBwdArgs {
+  const float* d_gain; const float* gain; const float* h_pre; const float* w1; const float* w2;
+  float* d_pre2;   // (B,C)
+  float* d_hpre;   // (B,R)
+  float* d_mean;   // (B,C)
+  int B, C, R;
+};
+int scalelong_backward(const ScaleLongBwdArgs& a, cudaStream_t stream);
+
+struct UncertaintyArgs {
+  const float* fourier; const float* w1; const float* w2; const float* gain;
+  float* aug_out; float* h_pre; float* h_out; float* u_raw; float* u;
+  int B, F;
+};
+int uncertainty_forward(const UncertaintyArgs& a, cudaStream_t stream);
+struct UncertaintyBwdArgs {
+  const float* g_u; const float* gain; const float* w2; const float* h_pre;
+  float* g_uraw; float* g_hpre;
+  int B, F;
+};
+int uncertainty_backward(const UncertaintyBwdArgs& a, cudaStream_t stream);
+
+int conv_in_im2col(const float* noisy, const float* sigma, int sigma_stride, float sigma_data, __nv_bfloat16* out, int B,
+                   int Ci, int H, int W, cudaStream_t stream);
+struct ConvOutArgs {
+  const __nv_bfloat16* x;   // (B,HW,C)
+  const __nv_bfloat16* w;   // w_hat bf16 [Co][C]
+  const float* gain_out;    // 0-d
+  const float* noisy;       // (B,Co,H,W) fp32
+  const float* sigma; int sigma_stride;
+  float sigma_data;
+  float* f_raw;             // (B,Co,H,W) raw conv output (saved for backward) or null
+  float* D;                 // (B,Co,H,W)
+  int B, HW, C, Co;
+};
+int conv_out_forward(const ConvOutArgs& a, cudaStream_t stream);
+struct ConvOutBwdArgs {
+  const float* g_D; const float* f_raw; const __nv_bfloat16* x; const __nv_bfloat16* w; const float* gain_out;
+  const float* sigma; int sigma_stride; float sigma_data;
+  __nv_bfloat16* g_x;   // (B,HW,C)
+  float* g_w;           // [Co][C] accumulated atomically (zero first)
+  float* g_gain_out;    // scalar accumulated atomically (zero first)
+  int B, HW, C, Co;
+};
+int conv_out_backward(const ConvOutBwdArgs& a, cudaStream_t stream);
+int wmse_forward(const float* D, const float* y, const float* sigma, const float* u, float sigma_data, float* mse,
+                 float* loss, int B, int n, cudaStream_t stream);
+int wmse_backward(const float* D, const float* y, const float* sigma, const float* u, const float* mse,
+                  const float* g_loss, float sigma_data, float* g_D, float* g_u, int B, int n, cudaStream_t stream);
+int heun_step(const float* x0, const float* x1, const float* D, const float* d_prev, float* x_out, float* d_out,
+              const float* ts, int step, int mode, long long n, cudaStream_t stream);
+int diffuse(const float* clean, const float* eps, const float* noise, float P_mean, float P_std, float* noisy,
+            float* sigma, int B, int n, cudaStream_t stream);
 
 }  // namespace tedm

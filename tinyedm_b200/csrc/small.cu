@@ -1,0 +1,623 @@
+// Small fp32 layers and image-sized kernels of the EDM2 hot path (launch-latency / HBM bound).
+//
+//   sgemm                 generic fp32 GEMM on CUDA cores for the autocast-off islands (Linear, networks.py:46-64)
+//   embedding_fwd/bwd     c_noise -> Fourier features -> sigma_embed -> class embed -> mp_add -> mp_silu
+//                         (networks.py:121-178)
+//   mod_finish fwd/bwd    m = embed(emb) * gain + 1 for all blocks at once (networks.py:255-258, :319-322)
+//   scalelong fwd/bwd     learned skip gain (networks.py:106-118)
+//   uncertainty fwd/bwd   log-variance head (networks.py:91-103)
+//   conv_in_im2col        c_in * x, ones channel and the 3x3 patch gather feeding the tensor-core GEMM
+//                         (networks.py:578-587)
+//   conv_out fwd/bwd      1x1 conv to image channels fused with D = c_skip x + c_out gain_out F (:602-603)
+//   wmse fwd/bwd          (uncertainty-)weighted MSE, metric.py:8-18 + edm.py:212-219
+//   heun_step, diffuse    solvers.py:45-57, edm.py:84-93
+#include "common.cuh"
+#include "kernels.h"
+
+namespace tedm {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// sgemm: C[M,N] = alpha * op(A) op(B) + beta * C   (row-major, explicit leading dimensions)
+// ------------------------------------------------------------------------------------------------
+constexpr int TS = 64, TK = 16;
+
+__global__ void __launch_bounds__(256)
+sgemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ C, int M, int N, int K,
+             int lda, int ldb, int ldc, int transA, int transB, float alpha, float beta) {
+  __shared__ float As[TK][TS + 1];
+  __shared__ float Bs[TK][TS + 1];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int m0 = blockIdx.y * TS, n0 = blockIdx.x * TS;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += TK) {
+    for (int i = threadIdx.x; i < TS * TK; i += 256) {
+      int mm, kk;
+      if (transA) { mm = i % TS; kk = i / TS; } else { kk = i % TK; mm = i / TK; }
+      const int gm = m0 + mm, gk = k0 + kk;
+      float v = 0.f;
+      if (gm < M && gk < K) v = transA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+      As[kk][mm] = v;
+    }
+    for (int i = threadIdx.x; i < TS * TK; i += 256) {
+      int nn, kk;
+      if (transB) { kk = i % TK; nn = i / TK; } else { nn = i % TS; kk = i / TS; }
+      const int gn = n0 + nn, gk = k0 + kk;
+      float v = 0.f;
+      if (gn < N && gk < K) v = transB ? Bm[(size_t)gn * ldb + gk] : Bm[(size_t)gk * ldb + gn];
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
+      if (gm < M && gn < N) {
+        float* c = C + (size_t)gm * ldc + gn;
+        *c = alpha * acc[i][j] + (beta != 0.f ? beta * *c : 0.f);
+      }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// embedding
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+embedding_fwd_kernel(const EmbeddingArgs a) {
+  extern __shared__ float four_s[];  // [F]
+  const int b = blockIdx.x;
+  const float sigma = a.sigma[a.sigma_stride * b];
+  const float c_noise = logf(sigma) * 0.25f;
+  for (int f = threadIdx.x; f < a.F; f += blockDim.x) {
+    const float v = cosf(c_noise * a.freqs[f] + a.phases[f]) * 1.41421356237f;
+    four_s[f] = v;
+    a.fourier[(size_t)b * a.F + f] = v;
+  }
+  __syncthreads();
+  const float t = a.add_factor;
+  const float inv_c = rsqrtf((1.f - t) * (1.f - t) + t * t);
+  for (int e = threadIdx.x; e < a.E; e += blockDim.x) {
+    const float* w = a.w_sigma + (size_t)e * a.F;
+    float acc = 0.f;
+    for (int f = 0; f < a.F; ++f) acc += w[f] * four_s[f];
+    if (a.labels != nullptr) {
+      const long long lab = a.labels[b];
+      const float cls = a.w_class[(size_t)e * a.n_classes + lab] * sqrtf((float)a.n_classes);
+      acc = ((1.f - t) * acc + t * cls) * inv_c;
+    }
+    a.pre[(size_t)b * a.E + e] = acc;
+    a.emb[(size_t)b * a.E + e] = mp_silu_f(acc);
+  }
+}
+
+// g_pre = g_emb * mp_silu'(pre); g_sig = g_pre * (1-t)/c (or g_pre); scatter class-weight gradient
+__global__ void __launch_bounds__(256)
+embedding_bwd_kernel(const EmbeddingBwdArgs a) {
+  const int b = blockIdx.x;
+  const float t = a.add_factor;
+  const float inv_c = rsqrtf((1.f - t) * (1.f - t) + t * t);
+  for (int e = threadIdx.x; e < a.E; e += blockDim.x) {
+    const float gp = a.g_emb[(size_t)b * a.E + e] * mp_silu_grad_f(a.pre[(size_t)b * a.E + e]);
+    if (a.labels != nullptr) {
+      a.g_sig[(size_t)b * a.E + e] = gp * (1.f - t) * inv_c;
+      const long long lab = a.labels[b];
+      atomicAdd(a.g_w_class + (size_t)e * a.n_classes + lab, gp * t * inv_c * sqrtf((float)a.n_classes));
+    } else {
+      a.g_sig[(size_t)b * a.E + e] = gp;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// modulation finish: m[b, col] = lin[b, col] * gain[blk(col)] + 1
+// ------------------------------------------------------------------------------------------------
+__global__ void mod_finish_fwd_kernel(const float* __restrict__ lin, const float* const* __restrict__ gains,
+                                      const int* __restrict__ col_block, float* __restrict__ m, int B, int N) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * N) return;
+  const int col = (int)(i % N);
+  m[i] = lin[i] * *gains[col_block[col]] + 1.0f;
+}
+
+// one CTA per block id: d_gain[blk] = sum dm*lin over its columns; d_lin = dm * gain
+__global__ void __launch_bounds__(256)
+mod_finish_bwd_kernel(const float* __restrict__ lin, const float* __restrict__ dm, const float* const* __restrict__ gains,
+                      const int* __restrict__ blk_start, float* __restrict__ d_lin, float* __restrict__ d_gain, int B,
+                      int N) {
+  __shared__ float red[8];
+  const int blk = blockIdx.x;
+  const int c0 = blk_start[blk], c1 = blk_start[blk + 1];
+  const int w = c1 - c0;
+  const float g = *gains[blk];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < B * w; i += blockDim.x) {
+    const int b = i / w, c = c0 + i - b * w;
+    const size_t o = (size_t)b * N + c;
+    const float d = dm[o];
+    acc += d * lin[o];
+    d_lin[o] = d * g;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    d_gain[blk] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ScaleLong MLP (per batch row)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+scalelong_fwd_kernel(const ScaleLongArgs a) {
+  extern __shared__ float sm[];  // aug[C+1], h[R]
+  float* aug = sm;
+  float* h = sm + a.C + 1;
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    const float v = a.mean[(size_t)b * a.C + c];
+    aug[c] = v;
+    a.aug_out[(size_t)b * (a.C + 1) + c] = v;
+  }
+  if (threadIdx.x == 0) {
+    aug[a.C] = 1.0f;
+    a.aug_out[(size_t)b * (a.C + 1) + a.C] = 1.0f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < a.R; j += blockDim.x / 32) {
+    const float* w = a.w1 + (size_t)j * (a.C + 1);
+    float acc = 0.f;
+    for (int c = lane; c <= a.C; c += 32) acc += w[c] * aug[c];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      a.h_pre[(size_t)b * a.R + j] = acc;
+      const float hv = mp_silu_f(acc);
+      h[j] = hv;
+      a.h_out[(size_t)b * a.R + j] = hv;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    const float* w = a.w2 + (size_t)c * a.R;
+    float acc = 0.f;
+    for (int j = 0; j < a.R; ++j) acc += w[j] * h[j];
+    a.gain[(size_t)b * a.C + c] = 1.0f / (1.0f + __expf(-acc));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+scalelong_bwd_kernel(const ScaleLongBwdArgs a) {
+  extern __shared__ float sm[];  // dp2[C], dhp[R]
+  float* dp2 = sm;
+  float* dhp = sm + a.C;
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    const float g = a.gain[(size_t)b * a.C + c];
+    const float v = a.d_gain[(size_t)b * a.C + c] * g * (1.0f - g);
+    dp2[c] = v;
+    a.d_pre2[(size_t)b * a.C + c] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = warp; j < a.R; j += blockDim.x / 32) {
+    float acc = 0.f;
+    for (int c = lane; c < a.C; c += 32) acc += dp2[c] * a.w2[(size_t)c * a.R + j];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float v = acc * mp_silu_grad_f(a.h_pre[(size_t)b * a.R + j]);
+      dhp[j] = v;
+      a.d_hpre[(size_t)b * a.R + j] = v;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < a.R; ++j) acc += dhp[j] * a.w1[(size_t)j * (a.C + 1) + c];
+    a.d_mean[(size_t)b * a.C + c] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// UncertaintyNet (per batch row); in = hidden = F
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+uncertainty_fwd_kernel(const UncertaintyArgs a) {
+  extern __shared__ float sm[];  // aug[F+1], h[F]
+  float* aug = sm;
+  float* h = sm + a.F + 1;
+  const int b = blockIdx.x;
+  for (int f = threadIdx.x; f < a.F; f += blockDim.x) {
+    const float v = a.fourier[(size_t)b * a.F + f];
+    aug[f] = v;
+    a.aug_out[(size_t)b * (a.F + 1) + f] = v;
+  }
+  if (threadIdx.x == 0) {
+    aug[a.F] = 1.0f;
+    a.aug_out[(size_t)b * (a.F + 1) + a.F] = 1.0f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < a.F; j += blockDim.x) {
+    const float* w = a.w1 + (size_t)j * (a.F + 1);
+    float acc = 0.f;
+    for (int f = 0; f <= a.F; ++f) acc += w[f] * aug[f];
+    a.h_pre[(size_t)b * a.F + j] = acc;
+    const float hv = mp_silu_f(acc);
+    h[j] = hv;
+    a.h_out[(size_t)b * a.F + j] = hv;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float acc = 0.f;
+    for (int j = threadIdx.x; j < a.F; j += 32) acc += a.w2[j] * h[j];
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) {
+      a.u_raw[b] = acc;
+      a.u[b] = acc * *a.gain;
+    }
+  }
+}
+
+// g_uraw[b] = g_u[b]*gain ; g_hpre[b,j] = g_uraw*w2[j]*silu'(h_pre)
+__global__ void __launch_bounds__(256)
+uncertainty_bwd_kernel(const UncertaintyBwdArgs a) {
+  const int b = blockIdx.x;
+  const float gr = a.g_u[b] * *a.gain;
+  if (threadIdx.x == 0) a.g_uraw[b] = gr;
+  for (int j = threadIdx.x; j < a.F; j += blockDim.x)
+    a.g_hpre[(size_t)b * a.F + j] = gr * a.w2[j] * mp_silu_grad_f(a.h_pre[(size_t)b * a.F + j]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_in im2col: (B,Ci,H,W) fp32 NCHW -> (B,H,W,64) bf16 patch matrix, k = tap*(Ci+1) + ci
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv_in_im2col_kernel(const float* __restrict__ noisy, const float* __restrict__ sigma, int sigma_stride,
+                      float sigma_data, __nv_bfloat16* __restrict__ out, int B, int Ci, int H, int W) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (pixel, group of 8 k)
+  const long long total = (long long)B * H * W * 8;
+  if (idx >= total) return;
+  const int g = (int)(idx & 7);
+  const long long pix = idx >> 3;
+  const int w = (int)(pix % W), h = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+  const float s = sigma[b * sigma_stride];
+  const float c_in = rsqrtf(sigma_data * sigma_data + s * s);
+  const int cin = Ci + 1;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = g * 8 + i;
+    float val = 0.f;
+    if (k < 9 * cin) {
+      const int tap = k / cin, ci = k - tap * cin;
+      const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+        val = ci < Ci ? c_in * noisy[(((long long)b * Ci + ci) * H + hh) * W + ww] : 1.0f;
+    }
+    v[i] = val;
+  }
+  uint4 o;
+  o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(out + pix * 64 + g * 8) = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_out (+ output preconditioning). One warp per pixel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxCo = 4;
+
+__global__ void __launch_bounds__(256)
+conv_out_fwd_kernel(const ConvOutArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long npix = (long long)a.B * a.HW;
+  if (warp >= npix) return;
+  const int b = (int)(warp / a.HW);
+  const int p = (int)(warp - (long long)b * a.HW);
+  float acc[kMaxCo] = {0.f, 0.f, 0.f, 0.f};
+  const __nv_bfloat16* xr = a.x + warp * a.C;
+  for (int c = lane * 2; c < a.C; c += 64) {
+    const float2 xv = unpack_bf16(*reinterpret_cast<const uint32_t*>(xr + c));
+#pragma unroll
+    for (int o = 0; o < kMaxCo; ++o)
+      if (o < a.Co) {
+        const float2 wv = unpack_bf16(*reinterpret_cast<const uint32_t*>(a.w + (size_t)o * a.C + c));
+        acc[o] += xv.x * wv.x + xv.y * wv.y;
+      }
+  }
+#pragma unroll
+  for (int o = 0; o < kMaxCo; ++o) acc[o] = warp_sum(acc[o]);
+  if (lane < a.Co) {
+    float f = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+    const float s = a.sigma[b * a.sigma_stride];
+    const float sd = a.sigma_data;
+    const float c_skip = sd * sd / (s * s + sd * sd);
+    const float c_out = s * sd * rsqrtf(s * s + sd * sd);
+    const size_t o = ((size_t)b * a.Co + lane) * a.HW + p;
+    if (a.f_raw != nullptr) a.f_raw[o] = f;
+    a.D[o] = f * (*a.gain_out) * c_out + a.noisy[o] * c_skip;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+conv_out_bwd_kernel(const ConvOutBwdArgs a) {
+  extern __shared__ float sm[];  // [warps][Co*C] partial dW
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long npix = (long long)a.B * a.HW;
+  const long long warp0 = (long long)blockIdx.x * nw + wib;
+  const long long nwarps = (long long)gridDim.x * nw;
+  const int per_lane = a.C / 32;  // channels per lane (C % 64 == 0 -> even)
+  float dw[kMaxCo][8];            // supports C <= 256 per lane chunk of 8; loop chunks otherwise
+  float dgain = 0.f;
+  const float gain_out = *a.gain_out;
+  // channel ownership: lane owns channels [lane*per_lane, (lane+1)*per_lane)
+  for (int cc = 0; cc < per_lane; cc += 8) {
+    const int nch = per_lane - cc < 8 ? per_lane - cc : 8;
+#pragma unroll
+    for (int o = 0; o < kMaxCo; ++o)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dw[o][i] = 0.f;
+    for (long long pix = warp0; pix < npix; pix += nwarps) {
+      const int b = (int)(pix / a.HW);
+      const int p = (int)(pix - (long long)b * a.HW);
+      const float s = a.sigma[b * a.sigma_stride];
+      const float sd = a.sigma_data;
+      const float c_out = s * sd * rsqrtf(s * s + sd * sd);
+      float gf[kMaxCo];
+#pragma unroll
+      for (int o = 0; o < kMaxCo; ++o) {
+        gf[o] = 0.f;
+        if (o < a.Co) {
+          const size_t oi = ((size_t)b * a.Co + o) * a.HW + p;
+          const float gd = a.g_D[oi] * c_out;
+          if (cc == 0 && lane == 0) dgain += gd * a.f_raw[oi];
+          gf[o] = gd * gain_out;
+        }
+      }
+      const int c0 = lane * per_lane + cc;
+      for (int i = 0; i < nch; ++i) {
+        const float xv = __bfloat162float(a.x[pix * a.C + c0 + i]);
+        float gx = 0.f;
+#pragma unroll
+        for (int o = 0; o < kMaxCo; ++o)
+          if (o < a.Co) {
+            dw[o][i] += gf[o] * xv;
+            gx += gf[o] * __bfloat162float(a.w[(size_t)o * a.C + c0 + i]);
+          }
+        a.g_x[pix * a.C + c0 + i] = __float2bfloat16_rn(gx);
+      }
+    }
+    // block reduction of dw over warps, then atomics
+    for (int o = 0; o < a.Co; ++o)
+      for (int i = 0; i < nch; ++i) sm[(size_t)wib * a.Co * a.C + (size_t)o * a.C + lane * per_lane + cc + i] = dw[o][i];
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < a.Co * a.C; idx += blockDim.x) {
+      const int c = idx % a.C;
+      const int lc = c % per_lane;
+      if (lc >= cc && lc < cc + nch) {
+        float t = 0.f;
+        for (int w2 = 0; w2 < nw; ++w2) t += sm[(size_t)w2 * a.Co * a.C + idx];
+        atomicAdd(a.g_w + idx, t);
+      }
+    }
+    __syncthreads();
+  }
+  dgain = warp_sum(dgain);
+  if (lane == 0 && dgain != 0.f) atomicAdd(a.g_gain_out, dgain);
+}
+
+// ------------------------------------------------------------------------------------------------
+// weighted MSE (+ uncertainty)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+wmse_fwd_kernel(const float* __restrict__ D, const float* __restrict__ y, const float* __restrict__ sigma,
+                const float* __restrict__ u, float sigma_data, float* __restrict__ mse, float* __restrict__ loss, int B,
+                int n) {
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  const float* d = D + (size_t)b * n;
+  const float* t = y + (size_t)b * n;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float e = d[i] - t[i];
+    acc += e * e;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    const float m = tot / (float)n;
+    mse[b] = m;
+    const float s = sigma[b];
+    float w = (s * s + sigma_data * sigma_data) / ((s * sigma_data) * (s * sigma_data));
+    float contrib = 0.f;
+    if (u != nullptr) {
+      w *= __expf(-u[b]);
+      contrib = u[b];
+    }
+    atomicAdd(loss, (w * m + contrib) / (float)B);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+wmse_bwd_kernel(const float* __restrict__ D, const float* __restrict__ y, const float* __restrict__ sigma,
+                const float* __restrict__ u, const float* __restrict__ mse, const float* __restrict__ g_loss,
+                float sigma_data, float* __restrict__ g_D, float* __restrict__ g_u, int B, int n) {
+  const int b = blockIdx.y;
+  const float s = sigma[b];
+  float w = (s * s + sigma_data * sigma_data) / ((s * sigma_data) * (s * sigma_data));
+  if (u != nullptr) w *= __expf(-u[b]);
+  const float gl = *g_loss;
+  const float k = gl * 2.0f * w / ((float)B * (float)n);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const size_t o = (size_t)b * n + i;
+    g_D[o] = k * (D[o] - y[o]);
+  }
+  if (u != nullptr && g_u != nullptr && blockIdx.x == 0 && threadIdx.x == 0) g_u[b] = gl * (1.0f - w * mse[b]) / (float)B;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Heun stages / initial scaling / diffusion
+// ------------------------------------------------------------------------------------------------
+__global__ void heun_step_kernel(const float* __restrict__ x0, const float* __restrict__ x1, const float* __restrict__ D,
+                                 const float* __restrict__ d_prev, float* __restrict__ x_out, float* __restrict__ d_out,
+                                 const float* __restrict__ ts, int step, int mode, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float t0 = ts[step], t1 = ts[step + 1];
+  if (mode == 0) {          // Euler predictor: d = (x0 - D)/t0 ; x1 = x0 + (t1 - t0) d        solvers.py:49-50
+    const float x = x0[i];
+    const float d = (x - D[i]) / t0;
+    d_out[i] = d;
+    x_out[i] = x + (t1 - t0) * d;
+  } else if (mode == 1) {   // trapezoidal corrector                                           solvers.py:56-57
+    const float dp = (x1[i] - D[i]) / t1;
+    x_out[i] = x0[i] + (t1 - t0) * (0.5f * d_prev[i] + 0.5f * dp);
+  } else {                  // x = x0 * t_0                                                     solvers.py:45
+    x_out[i] = x0[i] * t0;
+  }
+}
+
+__global__ void diffuse_kernel(const float* __restrict__ clean, const float* __restrict__ eps,
+                               const float* __restrict__ noise, float P_mean, float P_std, float* __restrict__ noisy,
+                               float* __restrict__ sigma, int B, int n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * n) return;
+  const int b = (int)(i / n);
+  const float s = __expf(P_mean + eps[b] * P_std);
+  if (i % n == 0) sigma[b] = s;
+  noisy[i] = clean[i] + noise[i] * s;
+}
+
+}  // namespace
+
+int sgemm(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
+          float alpha, float beta, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return 0;
+  dim3 grid((N + TS - 1) / TS, (M + TS - 1) / TS);
+  sgemm_kernel<<<grid, 256, 0, stream>>>(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, alpha, beta);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+
+int embedding_forward(const EmbeddingArgs& a, cudaStream_t stream) {
+  TEDM_CHECK(a.B > 0 && a.F > 0 && a.E > 0, "embedding: empty problem");
+  embedding_fwd_kernel<<<a.B, 256, a.F * sizeof(float), stream>>>(a);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+int embedding_backward(const EmbeddingBwdArgs& a, cudaStream_t stream) {
+  embedding_bwd_kernel<<<a.B, 256, 0, stream>>>(a);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+int mod_finish_forward(const float* lin, const float* const* gains, const int* col_block, float* m, int B, int N,
+                       cudaStream_t stream) {
+  const long long n = (long long)B * N;
+  mod_finish_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(lin, gains, col_block, m, B, N);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+int mod_finish_backward(const float* lin, const float* dm, const float* const* gains, const int* blk_start, float* d_lin,
+                        float* d_gain, int B, int N, int n_blocks, cudaStream_t stream) {
+  mod_finish_bwd_kernel<<<n_blocks, 256, 0, stream>>>(lin, dm, gains, blk_start, d_lin, d_gain, B, N);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+int scalelong_forward(const ScaleLongArgs& a, cudaStream_t stream) {
+  scalelong_fwd_kernel<<<a.B, 256, (a.C + 1 + a.R) * sizeof(float), stream>>>(a);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+int scalelong_backward(const ScaleLongBwdArgs& a, cudaStream_t stream) {
+  scalelong_bwd_kernel<<<a.B, 256, (a.C + a.R) * sizeof(float), stream>>>(a);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+int uncertainty_forward(const UncertaintyArgs& a, cudaStream_t stream) {
+  uncertainty_fwd_kernel<<<a.B, 256, (2 * a.F + 1) * sizeof(float), stream>>>(a);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+int uncertainty_backward(const UncertaintyBwdArgs& a, cudaStream_t stream) {
+  uncertainty_bwd_kernel<<<a.B, 256, 0, stream>>>(a);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+int conv_in_im2col(const float* noisy, const float* sigma, int sigma_stride, float sigma_data, __nv_bfloat16* out, int B,
+                   int Ci, int H, int W, cudaStream_t stream) {
+  TEDM_CHECK(9 * (Ci + 1) <= 64, "conv_in: at most 6 image channels supported (got %d)", Ci);
+  const long long total = (long long)B * H * W * 8;
+  conv_in_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(noisy, sigma, sigma_stride, sigma_data, out, B,
+                                                                            Ci, H, W);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+int conv_out_forward(const ConvOutArgs& a, cudaStream_t stream) {
+  TEDM_CHECK(a.Co >= 1 && a.Co <= kMaxCo && a.C % 64 == 0, "conv_out: unsupported Co=%d C=%d", a.Co, a.C);
+  const long long npix = (long long)a.B * a.HW;
+  conv_out_fwd_kernel<<<(unsigned)((npix + 7) / 8), 256, 0, stream>>>(a);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+int conv_out_backward(const ConvOutBwdArgs& a, cudaStream_t stream) {
+  TEDM_CHECK(a.Co >= 1 && a.Co <= kMaxCo && a.C % 64 == 0, "conv_out_bwd: unsupported Co=%d C=%d", a.Co, a.C);
+  const long long npix = (long long)a.B * a.HW;
+  long long blocks = (npix + 63) / 64;  // >= 8 pixels per warp
+  if (blocks > 2 * num_sms()) blocks = 2 * num_sms();
+  if (blocks < 1) blocks = 1;
+  const size_t smem = (size_t)8 * a.Co * a.C * sizeof(float);
+  TEDM_CHECK(smem <= 48 * 1024, "conv_out_bwd: C too large");
+  conv_out_bwd_kernel<<<(unsigned)blocks, 256, smem, stream>>>(a);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+int wmse_forward(const float* D, const float* y, const float* sigma, const float* u, float sigma_data, float* mse,
+                 float* loss, int B, int n, cudaStream_t stream) {
+  TEDM_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), stream));
+  wmse_fwd_kernel<<<B, 256, 0, stream>>>(D, y, sigma, u, sigma_data, mse, loss, B, n);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+int wmse_backward(const float* D, const float* y, const float* sigma, const float* u, const float* mse,
+                  const float* g_loss, float sigma_data, float* g_D, float* g_u, int B, int n, cudaStream_t stream) {
+  dim3 grid((n + 1023) / 1024 < 1 ? 1 : (n + 1023) / 1024, B);
+  wmse_bwd_kernel<<<grid, 256, 0, stream>>>(D, y, sigma, u, mse, g_loss, sigma_data, g_D, g_u, B, n);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+int heun_step(const float* x0, const float* x1, const float* D, const float* d_prev, float* x_out, float* d_out,
+              const float* ts, int step, int mode, long long n, cudaStream_t stream) {
+  heun_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x0, x1, D, d_prev, x_out, d_out, ts, step, mode, n);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+int diffuse(const float* clean, const float* eps, const float* noise, float P_mean, float P_std, float* noisy,
+            float* sigma, int B, int n, cudaStream_t stream) {
+  const long long tot = (long long)B * n;
+  diffuse_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(clean, eps, noise, P_mean, P_std, noisy, sigma, B, n);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tedm
