@@ -47,12 +47,15 @@ int tedm_weight_prep_backward(const tedm_weight_desc* table, int n, int total_ro
 /* The same entry computes the data gradient: pass g as x and the out_dgrad weight layout (Cin/Cout swapped).
  * epilogue: 0 plain (out = alpha*conv)
  *           1 modulation + mp_silu + dropout: out = drop(mp_silu(alpha*conv * mod[b,c]))  (networks.py:255-260, :319-324)
- *             raw (optional) receives the un-modulated conv output for backward
+ *             raw (optional) receives the un-modulated conv output for backward; the dropout mask is a counter-based
+ *             Philox stream keyed by seed (+ *seed_ptr, an optional DEVICE step counter so that a captured CUDA graph
+ *             draws a fresh mask on every replay)
  *           2 axpby: out = alpha*conv + beta*res; mp_add(x, conv, t) is alpha = t/c, beta = (1-t)/c,
  *             c = sqrt((1-t)^2+t^2)                                                     (networks.py:87-88, :263, :327) */
 int tedm_conv2d_forward(const void* x, const void* w, void* out, int B, int H, int W, int Cin, int Cout, int ksize,
                         int epilogue, float alpha, void* raw, const void* res, float beta, const float* mod,
-                        int mod_stride, float drop_p, uint64_t seed, int block_n, tedm_stream_t stream);
+                        int mod_stride, float drop_p, uint64_t seed, const uint64_t* seed_ptr, int block_n,
+                        tedm_stream_t stream);
 /* dL/dw_hat of the convolution above: dw[co][tap][ci] (=|+=) alpha * sum_p g[p,co] * x[p+tap,ci]  (autograd of :37) */
 int tedm_conv2d_wgrad(const void* g, const void* x, float* dw, int B, int H, int W, int Cin, int Cout, int ksize,
                       float alpha, int accumulate, int splits, tedm_stream_t stream);
@@ -69,7 +72,8 @@ int tedm_block_prep_backward(const void* g_res, float beta, const void* g_a, con
                              tedm_stream_t stream);
 /* backward of dropout(mp_silu(raw * mod[b,c])) (networks.py:255-261): g_raw, and d_mod[b,c] += sum_hw (zero d_mod first). */
 int tedm_modsilu_backward(const void* g_h, const void* raw, const float* mod, float* d_mod, void* g_raw, int B, int HW,
-                          int C, int mod_stride, float drop_p, uint64_t seed, tedm_stream_t stream);
+                          int C, int mod_stride, float drop_p, uint64_t seed, const uint64_t* seed_ptr,
+                          tedm_stream_t stream);
 /* out[b,c] += scale * sum_p A[b,p,a_off+c] * (Bm ? Bm[b,p,c] : 1)   (ScaleLong mean networks.py:115 and its adjoint) */
 int tedm_channel_dot(const void* A, const void* Bm, float* out, int B, int HW, int C, int CA, int a_off, float scale,
                      tedm_stream_t stream);
@@ -119,17 +123,39 @@ int tedm_conv_out_forward(const void* x, const void* w, const float* gain_out, c
 int tedm_conv_out_backward(const float* g_D, const float* f_raw, const void* x, const void* w, const float* gain_out,
                            const float* sigma, int sigma_stride, float sigma_data, void* g_x, float* g_w,
                            float* g_gain_out, int B, int HW, int C, int Co, tedm_stream_t stream);
-/* loss = sum_b w_b * mean_chw((D-y)^2) / B [+ mean(u)], w_b = lambda(sigma_b) [* exp(-u_b)]  (edm.py:212-219, metric.py:8-18) */
-int tedm_wmse_forward(const float* D, const float* y, const float* sigma, const float* u, float sigma_data, float* mse,
-                      float* loss, int B, int n, tedm_stream_t stream);
-int tedm_wmse_backward(const float* D, const float* y, const float* sigma, const float* u, const float* mse,
-                       const float* g_loss, float sigma_data, float* g_D, float* g_u, int B, int n, tedm_stream_t stream);
+/* loss = sum_b w_b * mean_chw((D-y)^2) / B [+ mean(u)]  (edm.py:212-219, metric.py:8-18), one fused reduction.
+ * w_b = weight[b] when `weight` is given (the WeightedMeanSquaredError(weight, preds, target) surface), otherwise
+ * lambda(sigma_b) [* exp(-u_b) when u is given]. mse: (B,) per-sample mean squared error (kept for backward);
+ * wsum (optional): += sum_b w_b*mse_b, the metric's running state (metric.py:44). */
+int tedm_wmse_forward(const float* D, const float* y, const float* sigma, const float* u, const float* weight,
+                      float sigma_data, float* mse, float* wsum, float* loss, int B, int n, tedm_stream_t stream);
+int tedm_wmse_backward(const float* D, const float* y, const float* sigma, const float* u, const float* weight,
+                       const float* mse, const float* g_loss, float sigma_data, float* g_D, float* g_u, float* g_weight,
+                       int B, int n, tedm_stream_t stream);
 /* Heun stages (solvers.py:45-57): mode 0 Euler predictor, 1 trapezoid corrector, 2 x*t_0; ts = device schedule */
 int tedm_heun_step(const float* x0, const float* x1, const float* D, const float* d_prev, float* x_out, float* d_out,
                    const float* ts, int step, int mode, int64_t n, tedm_stream_t stream);
 /* Diffuser.forward (edm.py:84-93) with the two normal draws supplied by the caller */
 int tedm_diffuse(const float* clean, const float* eps, const float* noise, float P_mean, float P_std, float* noisy,
                  float* sigma, int B, int n, tedm_stream_t stream);
+
+/* ---- optimiser step ("next" row N1): fused multi-tensor Adam + power-function EMA ----
+ * Replaces optim.Adam(fused=True) (edm.py:250-253) + EMAOptimizer.update (ema.py:137-140, :273) with ONE launch.
+ * table: DEVICE array of descriptors; chunks: DEVICE array of n_chunks (tensor index, chunk index) int32 pairs, one CTA
+ * per chunk of tedm_adam_chunk_elems() elements. step counts from 1 (Adam bias correction); the EMA decay is
+ * (1 - 1/step)^(gamma+1); gamma < 0 disables the EMA. hyper (optional, DEVICE {lr, step}) overrides lr/step so a
+ * captured CUDA graph can be replayed with new values. */
+typedef struct tedm_adam_desc {
+  void* p;       /* fp32 parameter            */
+  const void* g; /* fp32 gradient             */
+  void* m;       /* fp32 first moment         */
+  void* v;       /* fp32 second moment        */
+  void* ema;     /* fp32 EMA copy or NULL     */
+  int64_t n;     /* elements                  */
+} tedm_adam_desc;
+int tedm_adam_chunk_elems(void);
+int tedm_adam_ema_step(const tedm_adam_desc* table, const int32_t* chunks, int n_chunks, float lr, float step,
+                       const float* hyper, float beta1, float beta2, float eps, float gamma, tedm_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -81,6 +81,13 @@ def call(name: str, *args) -> None:
         raise RuntimeError(f"{name} failed ({rc}): {msg.decode() if msg else 'unknown error'}")
 
 
+def call_int(name: str, *args) -> int:
+    """For the few entry points whose return value is a quantity rather than a status (version, chunk size)."""
+    if _lib is None:
+        load()
+    return int(_fns[name](*args))
+
+
 def init_device(index: int) -> None:
     if index not in _initialised_devices:
         call("tedm_init", index)

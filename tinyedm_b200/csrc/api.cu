@@ -23,7 +23,8 @@ int tedm_init(int device) {
 
 int tedm_conv2d_forward(const void* x, const void* w, void* out, int B, int H, int W, int Cin, int Cout, int ksize,
                         int epilogue, float alpha, void* raw, const void* res, float beta, const float* mod,
-                        int mod_stride, float drop_p, uint64_t seed, int block_n, tedm_stream_t stream) {
+                        int mod_stride, float drop_p, uint64_t seed, const uint64_t* seed_ptr, int block_n,
+                        tedm_stream_t stream) {
   ConvGemmArgs a{};
   a.x = static_cast<const __nv_bfloat16*>(x);
   a.w = static_cast<const __nv_bfloat16*>(w);
@@ -34,6 +35,7 @@ int tedm_conv2d_forward(const void* x, const void* w, void* out, int B, int H, i
   a.res = static_cast<const __nv_bfloat16*>(res);
   a.beta = beta;
   a.mod = mod; a.mod_stride = mod_stride; a.drop_p = drop_p; a.seed = seed;
+  a.seed_ptr = reinterpret_cast<const unsigned long long*>(seed_ptr);
   a.block_n_override = block_n;
   return conv_gemm_launch(a, static_cast<cudaStream_t>(stream));
 }
@@ -74,9 +76,10 @@ int tedm_block_prep_backward(const void* g_res, float beta, const void* g_a, con
   return block_prep_backward(a, ST(stream));
 }
 int tedm_modsilu_backward(const void* g_h, const void* raw, const float* mod, float* d_mod, void* g_raw, int B, int HW,
-                          int C, int mod_stride, float drop_p, uint64_t seed, tedm_stream_t stream) {
+                          int C, int mod_stride, float drop_p, uint64_t seed, const uint64_t* seed_ptr,
+                          tedm_stream_t stream) {
   ModSiluBwdArgs a{CBF(g_h), CBF(raw), mod, d_mod, BF(g_raw), B, HW, C, mod_stride, drop_p, (uint32_t)seed,
-                   (uint32_t)(seed >> 32)};
+                   (uint32_t)(seed >> 32), reinterpret_cast<const unsigned long long*>(seed_ptr)};
   return modsilu_backward(a, ST(stream));
 }
 int tedm_channel_dot(const void* A, const void* Bm, float* out, int B, int HW, int C, int CA, int a_off, float scale,
@@ -156,13 +159,14 @@ int tedm_conv_out_backward(const float* g_D, const float* f_raw, const void* x, 
                    B, HW, C, Co};
   return conv_out_backward(a, ST(stream));
 }
-int tedm_wmse_forward(const float* D, const float* y, const float* sigma, const float* u, float sigma_data, float* mse,
-                      float* loss, int B, int n, tedm_stream_t stream) {
-  return wmse_forward(D, y, sigma, u, sigma_data, mse, loss, B, n, ST(stream));
+int tedm_wmse_forward(const float* D, const float* y, const float* sigma, const float* u, const float* weight,
+                      float sigma_data, float* mse, float* wsum, float* loss, int B, int n, tedm_stream_t stream) {
+  return wmse_forward(D, y, sigma, u, weight, sigma_data, mse, wsum, loss, B, n, ST(stream));
 }
-int tedm_wmse_backward(const float* D, const float* y, const float* sigma, const float* u, const float* mse,
-                       const float* g_loss, float sigma_data, float* g_D, float* g_u, int B, int n, tedm_stream_t stream) {
-  return wmse_backward(D, y, sigma, u, mse, g_loss, sigma_data, g_D, g_u, B, n, ST(stream));
+int tedm_wmse_backward(const float* D, const float* y, const float* sigma, const float* u, const float* weight,
+                       const float* mse, const float* g_loss, float sigma_data, float* g_D, float* g_u, float* g_weight,
+                       int B, int n, tedm_stream_t stream) {
+  return wmse_backward(D, y, sigma, u, weight, mse, g_loss, sigma_data, g_D, g_u, g_weight, B, n, ST(stream));
 }
 int tedm_heun_step(const float* x0, const float* x1, const float* D, const float* d_prev, float* x_out, float* d_out,
                    const float* ts, int step, int mode, int64_t n, tedm_stream_t stream) {
@@ -171,6 +175,12 @@ int tedm_heun_step(const float* x0, const float* x1, const float* D, const float
 int tedm_diffuse(const float* clean, const float* eps, const float* noise, float P_mean, float P_std, float* noisy,
                  float* sigma, int B, int n, tedm_stream_t stream) {
   return diffuse(clean, eps, noise, P_mean, P_std, noisy, sigma, B, n, ST(stream));
+}
+
+int tedm_adam_chunk_elems(void) { return adam_chunk_elems(); }
+int tedm_adam_ema_step(const tedm_adam_desc* table, const int32_t* chunks, int n_chunks, float lr, float step,
+                       const float* hyper, float beta1, float beta2, float eps, float gamma, tedm_stream_t stream) {
+  return adam_ema_step(table, chunks, n_chunks, lr, step, hyper, beta1, beta2, eps, gamma, ST(stream));
 }
 
 }  // extern "C"

@@ -168,6 +168,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int HW = p.H * p.W;
     int acc = 0;
     uint32_t acc_phase = 0;
+    // dropout seed = per-launch salt + a device-resident step counter (fresh masks under CUDA-graph replay)
+    unsigned long long seed64 = ((unsigned long long)p.seed_hi << 32) | p.seed_lo;
+    if (p.seed_ptr != nullptr) seed64 += *p.seed_ptr * 0x9E3779B97F4A7C15ull;
+    const uint32_t seed_lo = (uint32_t)seed64, seed_hi = (uint32_t)(seed64 >> 32);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       Tile t = decode_tile(p, tile);
       int n_this = p.Cout - t.n0;
@@ -207,11 +211,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int g = 0; g < 8; ++g) {
               if (c0 + g * 4 < n_this) {
                 float4 mm = *reinterpret_cast<const float4*>(mrow + g * 4);
-                // the stored (bf16) pre-modulation value is what backward sees; use it here too
-                float r0 = p.out2 ? bf16_round(v[g * 4 + 0]) : v[g * 4 + 0];
-                float r1 = p.out2 ? bf16_round(v[g * 4 + 1]) : v[g * 4 + 1];
-                float r2 = p.out2 ? bf16_round(v[g * 4 + 2]) : v[g * 4 + 2];
-                float r3 = p.out2 ? bf16_round(v[g * 4 + 3]) : v[g * 4 + 3];
+                // the reference's conv output is bf16 before the fp32 modulation island (networks.py:253-258);
+                // the stored (bf16) pre-modulation value is also what backward sees
+                float r0 = bf16_round(v[g * 4 + 0]);
+                float r1 = bf16_round(v[g * 4 + 1]);
+                float r2 = bf16_round(v[g * 4 + 2]);
+                float r3 = bf16_round(v[g * 4 + 3]);
                 v[g * 4 + 0] = mp_silu_f(r0 * mm.x);
                 v[g * 4 + 1] = mp_silu_f(r1 * mm.y);
                 v[g * 4 + 2] = mp_silu_f(r2 * mm.z);
@@ -222,10 +227,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               const float keep_scale = 1.0f / (1.0f - p.drop_p);
               const uint32_t thresh = (uint32_t)(p.drop_p * 4294967296.0);
               const unsigned long long e0 = (unsigned long long)pix * p.Cout + t.n0 + c0;
+              const uint32_t s_lo = seed_lo, s_hi = seed_hi;
 #pragma unroll
               for (int g = 0; g < 8; ++g) {
                 unsigned long long ctr = (e0 >> 2) + g;  // one Philox call per 4 consecutive channels
-                uint4 rnd = philox4x32((uint32_t)ctr, (uint32_t)(ctr >> 32), p.seed_lo, p.seed_hi);
+                uint4 rnd = philox4x32((uint32_t)ctr, (uint32_t)(ctr >> 32), s_lo, s_hi);
                 v[g * 4 + 0] = rnd.x >= thresh ? v[g * 4 + 0] * keep_scale : 0.f;
                 v[g * 4 + 1] = rnd.y >= thresh ? v[g * 4 + 1] * keep_scale : 0.f;
                 v[g * 4 + 2] = rnd.z >= thresh ? v[g * 4 + 2] * keep_scale : 0.f;
@@ -334,7 +340,7 @@ int conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t stream) {
   p.k_blocks = p.taps * (a.Cin / 64);
   p.epi = a.epi; p.alpha = a.alpha; p.out = a.out; p.out2 = a.out2; p.res = a.res;
   p.beta = a.beta; p.mod = a.mod; p.mod_stride = a.mod_stride;
-  p.drop_p = a.drop_p; p.seed_lo = (uint32_t)a.seed; p.seed_hi = (uint32_t)(a.seed >> 32);
+  p.drop_p = a.drop_p; p.seed_lo = (uint32_t)a.seed; p.seed_hi = (uint32_t)(a.seed >> 32); p.seed_ptr = a.seed_ptr;
   if (a.epi == EPI_MODSILU) TEDM_CHECK(a.mod != nullptr, "conv_gemm: MODSILU epilogue needs mod");
   if (a.epi == EPI_AXPBY) TEDM_CHECK(a.res != nullptr, "conv_gemm: AXPBY epilogue needs res");
 

@@ -34,6 +34,7 @@ struct ConvGemmArgs {
   int mod_stride;
   float drop_p;
   uint64_t seed;
+  const unsigned long long* seed_ptr;  // optional device step counter mixed into the seed
   int block_n_override;      // 0 = heuristic
 };
 
@@ -51,6 +52,7 @@ struct ConvGemmParams {
   int mod_stride;
   float drop_p;
   uint32_t seed_lo, seed_hi;
+  const unsigned long long* seed_ptr;
 };
 
 int conv_tile_geometry(int H, int W, int* RH, int* NB);
@@ -105,6 +107,7 @@ struct ModSiluBwdArgs {
   int B, HW, C, mod_stride;
   float drop_p;
   uint32_t seed_lo, seed_hi;
+  const unsigned long long* seed_ptr;
 };
 int modsilu_backward(const ModSiluBwdArgs& a, cudaStream_t stream);
 
@@ -208,13 +211,19 @@ struct ConvOutBwdArgs {
   int B, HW, C, Co;
 };
 int conv_out_backward(const ConvOutBwdArgs& a, cudaStream_t stream);
-int wmse_forward(const float* D, const float* y, const float* sigma, const float* u, float sigma_data, float* mse,
-                 float* loss, int B, int n, cudaStream_t stream);
-int wmse_backward(const float* D, const float* y, const float* sigma, const float* u, const float* mse,
-                  const float* g_loss, float sigma_data, float* g_D, float* g_u, int B, int n, cudaStream_t stream);
+int wmse_forward(const float* D, const float* y, const float* sigma, const float* u, const float* weight, float sigma_data,
+                 float* mse, float* wsum, float* loss, int B, int n, cudaStream_t stream);
+int wmse_backward(const float* D, const float* y, const float* sigma, const float* u, const float* weight, const float* mse,
+                  const float* g_loss, float sigma_data, float* g_D, float* g_u, float* g_weight, int B, int n,
+                  cudaStream_t stream);
 int heun_step(const float* x0, const float* x1, const float* D, const float* d_prev, float* x_out, float* d_out,
               const float* ts, int step, int mode, long long n, cudaStream_t stream);
 int diffuse(const float* clean, const float* eps, const float* noise, float P_mean, float P_std, float* noisy,
             float* sigma, int B, int n, cudaStream_t stream);
+
+// ---- optim.cu ----
+int adam_chunk_elems();
+int adam_ema_step(const tedm_adam_desc* table, const int32_t* chunks, int n_chunks, float lr, float step, const float* hyper,
+                  float beta1, float beta2, float eps, float gamma, cudaStream_t stream);
 
 }  // namespace tedm

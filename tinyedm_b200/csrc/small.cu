@@ -427,18 +427,37 @@ conv_out_bwd_kernel(const ConvOutBwdArgs a) {
 // ------------------------------------------------------------------------------------------------
 // weighted MSE (+ uncertainty)
 // ------------------------------------------------------------------------------------------------
+// weight_b = explicit weight[b] if given, else lambda(sigma_b) (edm.py:212) [* exp(-u_b) (edm.py:216)]
+__device__ __forceinline__ float wmse_weight(const float* weight, const float* sigma, const float* u, float sigma_data, int b) {
+  if (weight != nullptr) return weight[b];
+  const float s = sigma[b];
+  float w = (s * s + sigma_data * sigma_data) / ((s * sigma_data) * (s * sigma_data));
+  if (u != nullptr) w *= __expf(-u[b]);
+  return w;
+}
+
 __global__ void __launch_bounds__(256)
 wmse_fwd_kernel(const float* __restrict__ D, const float* __restrict__ y, const float* __restrict__ sigma,
-                const float* __restrict__ u, float sigma_data, float* __restrict__ mse, float* __restrict__ loss, int B,
-                int n) {
+                const float* __restrict__ u, const float* __restrict__ weight, float sigma_data, float* __restrict__ mse,
+                float* __restrict__ wsum, float* __restrict__ loss, int B, int n) {
   __shared__ float red[8];
   const int b = blockIdx.x;
   const float* d = D + (size_t)b * n;
   const float* t = y + (size_t)b * n;
   float acc = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float e = d[i] - t[i];
-    acc += e * e;
+  if ((n & 3) == 0) {
+    const float4* d4 = reinterpret_cast<const float4*>(d);
+    const float4* t4 = reinterpret_cast<const float4*>(t);
+    for (int i = threadIdx.x; i < n / 4; i += blockDim.x) {
+      const float4 a = d4[i], c = t4[i];
+      const float e0 = a.x - c.x, e1 = a.y - c.y, e2 = a.z - c.z, e3 = a.w - c.w;
+      acc += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float e = d[i] - t[i];
+      acc += e * e;
+    }
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -448,32 +467,30 @@ wmse_fwd_kernel(const float* __restrict__ D, const float* __restrict__ y, const 
     for (int i = 0; i < 8; ++i) tot += red[i];
     const float m = tot / (float)n;
     mse[b] = m;
-    const float s = sigma[b];
-    float w = (s * s + sigma_data * sigma_data) / ((s * sigma_data) * (s * sigma_data));
-    float contrib = 0.f;
-    if (u != nullptr) {
-      w *= __expf(-u[b]);
-      contrib = u[b];
-    }
+    const float w = wmse_weight(weight, sigma, u, sigma_data, b);
+    const float contrib = (weight == nullptr && u != nullptr) ? u[b] : 0.f;
+    if (wsum != nullptr) atomicAdd(wsum, w * m);               // metric.py:16-18 running state
     atomicAdd(loss, (w * m + contrib) / (float)B);
   }
 }
 
 __global__ void __launch_bounds__(256)
 wmse_bwd_kernel(const float* __restrict__ D, const float* __restrict__ y, const float* __restrict__ sigma,
-                const float* __restrict__ u, const float* __restrict__ mse, const float* __restrict__ g_loss,
-                float sigma_data, float* __restrict__ g_D, float* __restrict__ g_u, int B, int n) {
+                const float* __restrict__ u, const float* __restrict__ weight, const float* __restrict__ mse,
+                const float* __restrict__ g_loss, float sigma_data, float* __restrict__ g_D, float* __restrict__ g_u,
+                float* __restrict__ g_weight, int B, int n) {
   const int b = blockIdx.y;
-  const float s = sigma[b];
-  float w = (s * s + sigma_data * sigma_data) / ((s * sigma_data) * (s * sigma_data));
-  if (u != nullptr) w *= __expf(-u[b]);
+  const float w = wmse_weight(weight, sigma, u, sigma_data, b);
   const float gl = *g_loss;
   const float k = gl * 2.0f * w / ((float)B * (float)n);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const size_t o = (size_t)b * n + i;
     g_D[o] = k * (D[o] - y[o]);
   }
-  if (u != nullptr && g_u != nullptr && blockIdx.x == 0 && threadIdx.x == 0) g_u[b] = gl * (1.0f - w * mse[b]) / (float)B;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (weight == nullptr && u != nullptr && g_u != nullptr) g_u[b] = gl * (1.0f - w * mse[b]) / (float)B;
+    if (g_weight != nullptr) g_weight[b] = gl * mse[b] / (float)B;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -592,17 +609,21 @@ int conv_out_backward(const ConvOutBwdArgs& a, cudaStream_t stream) {
   TEDM_LAUNCH_CHECK();
   return 0;
 }
-int wmse_forward(const float* D, const float* y, const float* sigma, const float* u, float sigma_data, float* mse,
-                 float* loss, int B, int n, cudaStream_t stream) {
+int wmse_forward(const float* D, const float* y, const float* sigma, const float* u, const float* weight, float sigma_data,
+                 float* mse, float* wsum, float* loss, int B, int n, cudaStream_t stream) {
+  TEDM_CHECK(weight != nullptr || sigma != nullptr, "wmse: need either explicit weights or sigma");
+  TEDM_CHECK(B > 0 && n > 0, "wmse: empty batch");
   TEDM_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), stream));
-  wmse_fwd_kernel<<<B, 256, 0, stream>>>(D, y, sigma, u, sigma_data, mse, loss, B, n);
+  wmse_fwd_kernel<<<B, 256, 0, stream>>>(D, y, sigma, u, weight, sigma_data, mse, wsum, loss, B, n);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
-int wmse_backward(const float* D, const float* y, const float* sigma, const float* u, const float* mse,
-                  const float* g_loss, float sigma_data, float* g_D, float* g_u, int B, int n, cudaStream_t stream) {
+int wmse_backward(const float* D, const float* y, const float* sigma, const float* u, const float* weight, const float* mse,
+                  const float* g_loss, float sigma_data, float* g_D, float* g_u, float* g_weight, int B, int n,
+                  cudaStream_t stream) {
+  TEDM_CHECK(weight != nullptr || sigma != nullptr, "wmse: need either explicit weights or sigma");
   dim3 grid((n + 1023) / 1024 < 1 ? 1 : (n + 1023) / 1024, B);
-  wmse_bwd_kernel<<<grid, 256, 0, stream>>>(D, y, sigma, u, mse, g_loss, sigma_data, g_D, g_u, B, n);
+  wmse_bwd_kernel<<<grid, 256, 0, stream>>>(D, y, sigma, u, weight, mse, g_loss, sigma_data, g_D, g_u, g_weight, B, n);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
