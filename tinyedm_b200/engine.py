@@ -233,6 +233,7 @@ class DenoiserEngine:
         self.bank: WeightBank | None = None
         self.blocks: list[BlockPlan] = []
         self._aux_key = None
+        self.grad_sync = None   # set by parallel.DistributedEDM: overlaps the gradient all-reduce with this backward
         self._build_plan()
 
     # ---- static plan ----
@@ -449,12 +450,29 @@ class DenoiserEngine:
     # =====================================================================================================
     # backward
     # =====================================================================================================
-    def backward(self, ctx: dict, g_D: Tensor, *, need_g_emb: bool = True, on_block_done=None):
+    def ghat_units_backward_order(self) -> list[tuple[int, int]]:
+        """(start, end) element ranges of the flat g_hat buffer in the order `backward` completes them: the blocks from
+        last to first, then one trailing unit with everything in front of the first block (embed weights of all
+        blocks, conv_in, conv_out). Together they tile the whole buffer from its end to its start."""
+        self.bank.ensure_grad_buffers()
+        base = self.bank._ghat_flat.data_ptr()
+        def span(slots):
+            starts = [(s.ghat.data_ptr() - base) // 4 for s in slots]
+            return min(starts), max(st + _round_up(s.rows * s.kpad, _ALIGN) for st, s in zip(starts, slots))
+        units = []
+        for bp in reversed(self.blocks):
+            units.append(span([s for k, s in bp.w.items() if k != "embed"]))
+        first_block_start = units[-1][0]
+        units.append((0, first_block_start))
+        assert units[0][1] == self.bank._ghat_flat.numel()
+        return units
+
+    def backward(self, ctx: dict, g_D: Tensor, *, need_g_emb: bool = True):
         """Adjoint of `forward`. Fills every WeightSlot.grad, returns (g_emb, scalar_grads).
 
         scalar_grads: fp32 tensor [n_blocks + 1] = d(block gains..., gain_out).
-        on_block_done(i): optional callback after the weight g_hat of block i (in backward order) are complete —
-        the data-parallel wrapper uses it to start gradient all-reduces while the rest of backward still runs.
+        With `self.grad_sync` set (parallel.DistributedEDM) the g_hat regions are handed to the gradient all-reduce
+        as soon as their block is done, so the exchange overlaps the rest of this backward.
         """
         m = self.m
         ops.check(g_D, F32, "grad of denoised_image")
@@ -463,6 +481,9 @@ class DenoiserEngine:
         sigma = ctx["sigma"]
         nb = len(self.blocks)
         sg = torch.zeros(nb + 1, device=dev, dtype=F32)
+        sync = self.grad_sync
+        if sync is not None:
+            sync.backward_started()
         self.s_out.ghat.zero_()
         g = ops.conv_out_backward(g_D, ctx["f_raw"], ctx["x_last"], self.s_out.fwd, m.gain_out, sigma,
                                   float(m.sigma_data), self.s_out.ghat, sg[nb:])
@@ -470,8 +491,8 @@ class DenoiserEngine:
         pending: dict[int, Tensor] = {}
         for bp, S in zip(reversed(self.blocks), reversed(ctx["blocks"])):
             g = self._block_backward(bp, S, g, ctx, d_mod, pending)
-            if on_block_done is not None:
-                on_block_done(bp)
+            if sync is not None:
+                sync.unit_done()
         # conv_in weight gradient (its input is the image: no data gradient needed)
         ops.conv2d_wgrad(g, ctx["xcol"], self.s_in.ghat, 1)
         # modulation adjoint: d_mod -> block gains, embed weights, embedding
@@ -486,7 +507,12 @@ class DenoiserEngine:
         first = self.embed_slots[0]
         gh_all = self.bank._ghat_flat[first.ghat.storage_offset():first.ghat.storage_offset() + N * E].view(N, E)
         ops.sgemm(d_lin, emb, gh_all, N, E, B, N, E, E, True, False)
+        if sync is not None:
+            sync.unit_done()                 # trailing unit: embed weights, conv_in, conv_out
+            sync.before_weight_jacobian()
         self.bank.backward()
+        if sync is not None:
+            sync.reduce_scalars(sg)
         return g_emb, sg
 
     def _take_g_in(self, bp: BlockPlan, pending: dict, shape, dev):
