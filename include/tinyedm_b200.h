@@ -35,7 +35,11 @@ typedef struct tedm_weight_desc {
   void* out_dgrad;   /* bf16 w_hat [cin][taps flipped][rows]                      or NULL      */
   void* out_f32;     /* fp32 w_hat [rows][cin*taps]                               or NULL      */
   void* stats;       /* fp32 [rows][2] = {1/(eps*sqrt(n)+||w||), ||w||}                        */
-  int32_t rows, cin, taps, kpad, row_start, reserved[3];
+  int32_t rows, cin, taps, kpad, row_start;
+  int32_t qkv_head_dim; /* != 0: qkv conv of CosineAttention — prepared rows are permuted from the reference's
+                           head*3*hd + d*3 + {q,k,v} (networks.py:194) to {q,k,v}*C + head*hd + d, so the conv emits
+                           de-interleaved q | k | v planes; out_fwd / out_dgrad / g_hat use the permuted row index */
+  int32_t reserved[2];
 } tedm_weight_desc;
 /* table: DEVICE array of n descriptors ordered by row_start; total_rows = sum(rows).
  * training != 0 additionally rewrites every parameter in place: w <- normalize(w)  (networks.py:32-34). */
@@ -78,13 +82,16 @@ int tedm_modsilu_backward(const void* g_h, const void* raw, const float* mod, fl
 int tedm_channel_dot(const void* A, const void* Bm, float* out, int B, int HW, int C, int CA, int a_off, float scale,
                      tedm_stream_t stream);
 
-/* ---- cosine attention core (networks.py:194-202): qkv (B,S,3C) interleaved -> y (B,S,C) ---- */
-/* qkvn: workspace [3][B][heads][S][hd] bf16 (normalised q,k,v, kept for backward); lse: (B*heads*S) fp32 */
-int tedm_attention_forward(const void* qkv, void* qkvn, void* y, float* lse, int B, int S, int heads, int head_dim,
+/* ---- cosine attention core (networks.py:194-202): pixel_norm over head_dim of q, k and v, then
+ *      softmax(q k^T / sqrt(hd)) v, flash-style (no S x S matrix in memory) ----
+ * qkv: (B,S,3C) bf16 with channel = {q,k,v}*C + head*hd + d (the layout the qkv conv emits when its weight rows are
+ * permuted by the weight bank, see tedm_weight_desc.qkv_head_dim); y: (B,S,C), channel = head*hd + d (networks.py:202);
+ * lse: (B*heads*S) fp32 log-sum-exp kept for backward (may be NULL in inference). The normalisation and its
+ * backward are fused into the kernels: no normalised copy of q,k,v exists in HBM. delta_ws: (B*heads*S) fp32. */
+int tedm_attention_forward(const void* qkv, void* y, float* lse, int B, int S, int heads, int head_dim,
                            tedm_stream_t stream);
-int tedm_attention_backward(const void* qkv, const void* qkvn, const void* y, const void* g_y, const float* lse,
-                            float* delta_ws, void* g_qkvn_ws, void* g_qkv, int B, int S, int heads, int head_dim,
-                            tedm_stream_t stream);
+int tedm_attention_backward(const void* qkv, const void* y, const void* g_y, const float* lse, float* delta_ws,
+                            void* g_qkv, int B, int S, int heads, int head_dim, tedm_stream_t stream);
 
 /* ---- small fp32 layers ---- */
 /* C[M,N] = alpha*op(A)*op(B) + beta*C, row-major fp32 (F.linear of the autocast-off islands, networks.py:46-64) */

@@ -398,7 +398,7 @@ def test_fused_adam_ema_vs_torch(dev):
     import tinyedm_b200 as T
     torch.manual_seed(0)
     shapes = [(256, 256, 3, 3), (257,), (), (16, 257, 1, 1), (100003,)]
-    ps = [torch.nn.Parameter(torch.randn(*s, device=dev)) for s in shapes]
+    ps = [torch.nn.Parameter(torch.randn(s, device=dev)) for s in shapes]
     qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
     opt = T.FusedAdamEMA(ps, lr=0.02, betas=(0.9, 0.999), ema_length=0.13)
     ref = torch.optim.Adam(qs, lr=0.02, betas=(0.9, 0.999))
@@ -413,9 +413,9 @@ def test_fused_adam_ema_vs_torch(dev):
         for e, q in zip(ema, qs):
             e.mul_(decay).add_(q.detach(), alpha=1 - decay)
     for p, q in zip(ps, qs):
-        assert rel(p, q) < 1e-6
+        assert rel(p, q) < 5e-6    # powf-based bias correction in fp32 vs torch's double
     for e, e2 in zip(ema, opt.ema_params):
-        assert rel(e2, e) < 1e-6
+        assert rel(e2, e) < 5e-6
 
 
 def test_unsupported_inputs_fail_loudly(dev):
@@ -433,3 +433,41 @@ def test_unsupported_inputs_fail_loudly(dev):
         den(torch.zeros(2, 3, 16, 16), torch.ones(2), torch.zeros(2, 64))     # CPU tensors: no fallback
     with pytest.raises(RuntimeError):
         den(torch.zeros(2, 5, 16, 16, device=dev), torch.ones(2, device=dev), torch.zeros(2, 64, device=dev))
+
+
+def test_mnist_config_forward_backward_vs_oracle(dev):
+    """BASELINE configs[0]: the MNIST arch (mnist.yaml:39-43, 87.2 M parameters; 28/14/7 feature maps, channel changes with
+    conv_1x1 in the encoder, head_dim 64 at S=196 and 128 at S=49), class-conditional, batch 2, forward and backward."""
+    import dataclasses
+    import tinyedm_b200 as T
+    cfg = dict(O.MNIST)
+    cfg["denoiser"] = dataclasses.replace(cfg["denoiser"], dropout_rate=0.0)
+    dp, ep, _ = seeded_params(cfg, seed=7)
+    den, emb_m, _ = build_modules(cfg, dp, ep, None, dev)
+    den.eval(); emb_m.eval()
+    assert sum(p.numel() for p in den.parameters()) + sum(p.numel() for p in emb_m.parameters()) == 87_194_724
+    g = torch.Generator().manual_seed(2)
+    clean = (0.5 * torch.randn(2, 1, 28, 28, generator=g)).clamp(-1, 1)
+    noisy = clean + torch.randn(2, 1, 28, 28, generator=g) * torch.tensor([0.3, 2.0]).view(2, 1, 1, 1)
+    sigma = torch.tensor([0.3, 2.0])
+    labels = torch.tensor([3, 8])
+    dpo = {k: v.clone().requires_grad_(True) for k, v in dp.items()}
+    _, emb = O.embedding_forward(ep, cfg["embedding"], sigma, labels)
+    taps_o = {}
+    D_o = O.denoiser_forward(dpo, cfg["denoiser"], noisy, sigma, emb, taps=taps_o)
+    loss_o = O.training_loss(O.loss_weight(sigma, 0.5), D_o, clean)
+    loss_o.backward()
+    _, e = emb_m(sigma.to(dev), labels.to(dev))
+    D = den(noisy.to(dev), sigma.to(dev), e)
+    loss = T.fused_edm_loss(D, clean.to(dev), sigma.to(dev), 0.5)
+    loss.backward()
+    assert rel(D, D_o) < DRIFT_TOL and rel(loss, loss_o) < DRIFT_TOL
+    worst = ("", 0.0)
+    for k, p in den.named_parameters():
+        if p.ndim == 0:
+            continue
+        r = rel(p.grad, dpo[k].grad)
+        if r > worst[1]:
+            worst = (k, r)
+    print(f"MNIST config: D rel {rel(D, D_o):.2e}, worst tensor-gradient error {worst[1]:.2e} ({worst[0]})")
+    assert worst[1] < 6e-2, worst

@@ -27,7 +27,7 @@ class WeightDesc(ctypes.Structure):
         ("w", c_void_p), ("grad", c_void_p), ("g_hat", c_void_p), ("out_fwd", c_void_p), ("out_dgrad", c_void_p),
         ("out_f32", c_void_p), ("stats", c_void_p),
         ("rows", ctypes.c_int32), ("cin", ctypes.c_int32), ("taps", ctypes.c_int32), ("kpad", ctypes.c_int32),
-        ("row_start", ctypes.c_int32), ("reserved", ctypes.c_int32 * 3),
+        ("row_start", ctypes.c_int32), ("qkv_head_dim", ctypes.c_int32), ("reserved", ctypes.c_int32 * 2),
     ]
 
 

@@ -87,15 +87,13 @@ int tedm_channel_dot(const void* A, const void* Bm, float* out, int B, int HW, i
   ChannelDotArgs a{CBF(A), CBF(Bm), out, B, HW, C, CA, a_off, scale};
   return channel_dot(a, ST(stream));
 }
-int tedm_attention_forward(const void* qkv, void* qkvn, void* y, float* lse, int B, int S, int heads, int head_dim,
+int tedm_attention_forward(const void* qkv, void* y, float* lse, int B, int S, int heads, int head_dim,
                            tedm_stream_t stream) {
-  return attention_forward(CBF(qkv), BF(qkvn), BF(y), lse, B, S, heads, head_dim, ST(stream));
+  return attention_forward(CBF(qkv), BF(y), lse, B, S, heads, head_dim, ST(stream));
 }
-int tedm_attention_backward(const void* qkv, const void* qkvn, const void* y, const void* g_y, const float* lse,
-                            float* delta_ws, void* g_qkvn_ws, void* g_qkv, int B, int S, int heads, int head_dim,
-                            tedm_stream_t stream) {
-  return attention_backward(CBF(qkv), CBF(qkvn), CBF(y), CBF(g_y), lse, delta_ws, BF(g_qkvn_ws), BF(g_qkv), B, S, heads,
-                            head_dim, ST(stream));
+int tedm_attention_backward(const void* qkv, const void* y, const void* g_y, const float* lse, float* delta_ws,
+                            void* g_qkv, int B, int S, int heads, int head_dim, tedm_stream_t stream) {
+  return attention_backward(CBF(qkv), CBF(y), CBF(g_y), lse, delta_ws, BF(g_qkv), B, S, heads, head_dim, ST(stream));
 }
 int tedm_sgemm(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int transA,
                int transB, float alpha, float beta, tedm_stream_t stream) {

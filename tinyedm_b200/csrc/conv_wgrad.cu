@@ -220,8 +220,8 @@ int conv_wgrad_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   p.items = p.co_blks * p.ci_blks * p.taps;
   int splits = a.splits_override;
   if (splits <= 0) {
-    int target = 2 * num_sms();
-    splits = (target + p.items - 1) / p.items;
+    // one CTA per SM (192 KB of operand stages each): aim for exactly one full wave, never a ragged second one
+    splits = num_sms() / p.items;
   }
   if (splits > p.p_tiles) splits = p.p_tiles;
   if (splits < 1) splits = 1;

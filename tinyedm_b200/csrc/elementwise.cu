@@ -15,7 +15,7 @@ namespace tedm {
 
 namespace {
 
-constexpr int kMaxVec = 6;  // 6 * 32 lanes * 8 channels = 1536 channels max
+constexpr int kMaxVec = 6;  // 6 * 32 lanes * 8 channels = 1536 channels max (kernels are templated on the actual count)
 constexpr float kEps = 1e-4f;
 
 struct Vec8 {
@@ -45,6 +45,7 @@ __device__ __forceinline__ Vec8 load8f(const float* p) {
 // ------------------------------------------------------------------------------------------------
 // block_prep forward
 // ------------------------------------------------------------------------------------------------
+template <int NV>
 __global__ void __launch_bounds__(256)
 block_prep_fwd_kernel(const PrepArgs a) {
   const int H = a.resample == 1 ? a.Hin / 2 : (a.resample == 2 ? a.Hin * 2 : a.Hin);
@@ -59,10 +60,10 @@ block_prep_fwd_kernel(const PrepArgs a) {
     const int w = (int)(pix % W);
     const int h = (int)((pix / W) % H);
     const int b = (int)(pix / ((long long)W * H));
-    Vec8 val[kMaxVec];
+    Vec8 val[NV];
     float ss = 0.f;
 #pragma unroll
-    for (int it = 0; it < kMaxVec; ++it) {
+    for (int it = 0; it < NV; ++it) {
       const int v = lane + it * 32;
       if (v < nvec) {
         const int c0 = v * 8;
@@ -99,7 +100,7 @@ block_prep_fwd_kernel(const PrepArgs a) {
       if (a.nrm_out != nullptr && lane == 0) a.nrm_out[pix] = n;
     }
 #pragma unroll
-    for (int it = 0; it < kMaxVec; ++it) {
+    for (int it = 0; it < NV; ++it) {
       const int v = lane + it * 32;
       if (v < nvec) {
         Vec8 x = val[it];
@@ -125,12 +126,13 @@ block_prep_fwd_kernel(const PrepArgs a) {
 //   pixel_norm: g_u = g/n - x * sum_c(g*x) / ((n - eps) * C)
 //   resample adjoint, concat split: g_in = g_u[:C1] ; g_skip = g_u[C1:] * gain (+ d_mean/(Hin*Win))
 // ------------------------------------------------------------------------------------------------
+template <int NV>
 __device__ __forceinline__ void prep_bwd_pixel_grad(const PrepBwdArgs& a, long long pix, int C, int lane, int nvec,
-                                                    Vec8 (&g)[kMaxVec]) {
+                                                    Vec8 (&g)[NV]) {
   float dot = 0.f;
-  Vec8 xs[kMaxVec];
+  Vec8 xs[NV];
 #pragma unroll
-  for (int it = 0; it < kMaxVec; ++it) {
+  for (int it = 0; it < NV; ++it) {
     const int v = lane + it * 32;
     if (v < nvec) {
       const long long o = pix * C + v * 8;
@@ -161,7 +163,7 @@ __device__ __forceinline__ void prep_bwd_pixel_grad(const PrepBwdArgs& a, long l
     const float inv_n = 1.0f / n;
     const float k = dot / (fmaxf(n - kEps, 1e-20f) * (float)C);
 #pragma unroll
-    for (int it = 0; it < kMaxVec; ++it) {
+    for (int it = 0; it < NV; ++it) {
       const int v = lane + it * 32;
       if (v < nvec) {
 #pragma unroll
@@ -208,6 +210,7 @@ __device__ __forceinline__ void prep_bwd_store(const PrepBwdArgs& a, int b, long
   }
 }
 
+template <int NV>
 __global__ void __launch_bounds__(256)
 block_prep_bwd_kernel(const PrepBwdArgs a) {
   const int H = a.resample == 1 ? a.Hin / 2 : (a.resample == 2 ? a.Hin * 2 : a.Hin);
@@ -224,24 +227,24 @@ block_prep_bwd_kernel(const PrepBwdArgs a) {
       const int ws = (int)(sp % a.Win);
       const int hs = (int)((sp / a.Win) % a.Hin);
       const int b = (int)(sp / ((long long)a.Win * a.Hin));
-      Vec8 tot[kMaxVec];
+      Vec8 tot[NV];
 #pragma unroll
-      for (int it = 0; it < kMaxVec; ++it)
+      for (int it = 0; it < NV; ++it)
 #pragma unroll
         for (int i = 0; i < 8; ++i) tot[it].v[i] = 0.f;
       for (int dy = 0; dy < 2; ++dy)
         for (int dx = 0; dx < 2; ++dx) {
           const long long pix = ((long long)b * H + 2 * hs + dy) * W + 2 * ws + dx;
-          Vec8 g[kMaxVec];
-          prep_bwd_pixel_grad(a, pix, C, lane, nvec, g);
+          Vec8 g[NV];
+          prep_bwd_pixel_grad<NV>(a, pix, C, lane, nvec, g);
 #pragma unroll
-          for (int it = 0; it < kMaxVec; ++it)
+          for (int it = 0; it < NV; ++it)
             if (lane + it * 32 < nvec)
 #pragma unroll
               for (int i = 0; i < 8; ++i) tot[it].v[i] += g[it].v[i];
         }
 #pragma unroll
-      for (int it = 0; it < kMaxVec; ++it) {
+      for (int it = 0; it < NV; ++it) {
         const int v = lane + it * 32;
         if (v < nvec) prep_bwd_store(a, b, sp, v, tot[it], 1.0f);
       }
@@ -252,10 +255,10 @@ block_prep_bwd_kernel(const PrepBwdArgs a) {
       const int w = (int)(pix % W);
       const int h = (int)((pix / W) % H);
       const int b = (int)(pix / ((long long)W * H));
-      Vec8 g[kMaxVec];
-      prep_bwd_pixel_grad(a, pix, C, lane, nvec, g);
+      Vec8 g[NV];
+      prep_bwd_pixel_grad<NV>(a, pix, C, lane, nvec, g);
 #pragma unroll
-      for (int it = 0; it < kMaxVec; ++it) {
+      for (int it = 0; it < NV; ++it) {
         const int v = lane + it * 32;
         if (v < nvec) {
           if (a.resample == 1) {
@@ -380,7 +383,7 @@ channel_dot_kernel(const ChannelDotArgs a) {
 
 int grid_for_warps(long long nwarps_needed, int warps_per_block) {
   long long blocks = (nwarps_needed + warps_per_block - 1) / warps_per_block;
-  long long cap = (long long)num_sms() * 16;
+  long long cap = (long long)num_sms() * 32;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
@@ -397,7 +400,15 @@ int block_prep_forward(const PrepArgs& a, cudaStream_t stream) {
   const int W = a.resample == 1 ? a.Win / 2 : (a.resample == 2 ? a.Win * 2 : a.Win);
   const long long npix = (long long)a.B * H * W;
   if (npix == 0) return 0;
-  block_prep_fwd_kernel<<<grid_for_warps(npix, 8), 256, 0, stream>>>(a);
+  const int nv = (C / 8 + 31) / 32;
+  const int grid = grid_for_warps(npix, 8);
+  switch (nv) {
+    case 1: block_prep_fwd_kernel<1><<<grid, 256, 0, stream>>>(a); break;
+    case 2: block_prep_fwd_kernel<2><<<grid, 256, 0, stream>>>(a); break;
+    case 3: block_prep_fwd_kernel<3><<<grid, 256, 0, stream>>>(a); break;
+    case 4: block_prep_fwd_kernel<4><<<grid, 256, 0, stream>>>(a); break;
+    default: block_prep_fwd_kernel<6><<<grid, 256, 0, stream>>>(a); break;
+  }
   TEDM_LAUNCH_CHECK();
   return 0;
 }
@@ -410,7 +421,15 @@ int block_prep_backward(const PrepBwdArgs& a, cudaStream_t stream) {
   TEDM_CHECK(!(a.g_a != nullptr && a.x == nullptr), "block_prep_bwd: g_a needs x");
   const long long npix = a.resample == 1 ? (long long)a.B * (a.Hin / 2) * (a.Win / 2) : (long long)a.B * a.Hin * a.Win;
   if (npix == 0) return 0;
-  block_prep_bwd_kernel<<<grid_for_warps(npix, 8), 256, 0, stream>>>(a);
+  const int nv = (C / 8 + 31) / 32;
+  const int grid = grid_for_warps(npix, 8);
+  switch (nv) {
+    case 1: block_prep_bwd_kernel<1><<<grid, 256, 0, stream>>>(a); break;
+    case 2: block_prep_bwd_kernel<2><<<grid, 256, 0, stream>>>(a); break;
+    case 3: block_prep_bwd_kernel<3><<<grid, 256, 0, stream>>>(a); break;
+    case 4: block_prep_bwd_kernel<4><<<grid, 256, 0, stream>>>(a); break;
+    default: block_prep_bwd_kernel<6><<<grid, 256, 0, stream>>>(a); break;
+  }
   TEDM_LAUNCH_CHECK();
   return 0;
 }

@@ -121,11 +121,10 @@ struct ChannelDotArgs {
 int channel_dot(const ChannelDotArgs& a, cudaStream_t stream);
 
 // ---- attention.cu ----
-int attention_forward(const __nv_bfloat16* qkv, __nv_bfloat16* qkvn, __nv_bfloat16* y, float* lse, int B, int S,
-                      int heads, int hd, cudaStream_t stream);
-int attention_backward(const __nv_bfloat16* qkv, const __nv_bfloat16* qkvn, const __nv_bfloat16* y,
-                       const __nv_bfloat16* g_y, const float* lse, float* delta, __nv_bfloat16* g_qkvn,
-                       __nv_bfloat16* g_qkv, int B, int S, int heads, int hd, cudaStream_t stream);
+int attention_forward(const __nv_bfloat16* qkv, __nv_bfloat16* y, float* lse, int B, int S, int heads, int hd,
+                      cudaStream_t stream);
+int attention_backward(const __nv_bfloat16* qkv, const __nv_bfloat16* y, const __nv_bfloat16* g_y, const float* lse,
+                       float* delta, __nv_bfloat16* g_qkv, int B, int S, int heads, int hd, cudaStream_t stream);
 
 // ---- small.cu ----
 int sgemm(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,

@@ -25,19 +25,23 @@ constexpr int TS = 64, TK = 16;
 
 __global__ void __launch_bounds__(256)
 sgemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ C, int M, int N, int K,
-             int lda, int ldb, int ldc, int transA, int transB, float alpha, float beta) {
+             int lda, int ldb, int ldc, int transA, int transB, float alpha, float beta, int k_chunk) {
   __shared__ float As[TK][TS + 1];
   __shared__ float Bs[TK][TS + 1];
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   const int m0 = blockIdx.y * TS, n0 = blockIdx.x * TS;
+  // split-K: blockIdx.z owns K range [k_begin, k_end); partial results are combined with atomics into a zeroed C
+  const int k_begin = blockIdx.z * k_chunk;
+  const int k_end = min(K, k_begin + k_chunk);
+  const bool split = gridDim.z > 1;
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += TK) {
+  for (int k0 = k_begin; k0 < k_end; k0 += TK) {
     for (int i = threadIdx.x; i < TS * TK; i += 256) {
       int mm, kk;
       if (transA) { mm = i % TS; kk = i / TS; } else { kk = i % TK; mm = i / TK; }
       const int gm = m0 + mm, gk = k0 + kk;
       float v = 0.f;
-      if (gm < M && gk < K) v = transA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+      if (gm < M && gk < k_end) v = transA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
       As[kk][mm] = v;
     }
     for (int i = threadIdx.x; i < TS * TK; i += 256) {
@@ -45,7 +49,7 @@ sgemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* _
       if (transB) { kk = i % TK; nn = i / TK; } else { nn = i % TS; kk = i / TS; }
       const int gn = n0 + nn, gk = k0 + kk;
       float v = 0.f;
-      if (gn < N && gk < K) v = transB ? Bm[(size_t)gn * ldb + gk] : Bm[(size_t)gk * ldb + gn];
+      if (gn < N && gk < k_end) v = transB ? Bm[(size_t)gn * ldb + gk] : Bm[(size_t)gk * ldb + gn];
       Bs[kk][nn] = v;
     }
     __syncthreads();
@@ -70,7 +74,8 @@ sgemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* _
       const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
       if (gm < M && gn < N) {
         float* c = C + (size_t)gm * ldc + gn;
-        *c = alpha * acc[i][j] + (beta != 0.f ? beta * *c : 0.f);
+        if (split) atomicAdd(c, alpha * acc[i][j]);
+        else *c = alpha * acc[i][j] + (beta != 0.f ? beta * *c : 0.f);
       }
     }
 }
@@ -532,7 +537,24 @@ int sgemm(const float* A, const float* B, float* C, int M, int N, int K, int lda
           float alpha, float beta, cudaStream_t stream) {
   if (M <= 0 || N <= 0) return 0;
   dim3 grid((N + TS - 1) / TS, (M + TS - 1) / TS);
-  sgemm_kernel<<<grid, 256, 0, stream>>>(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, alpha, beta);
+  // long-K, few-tile problems (e.g. g_emb = d_lin (B x 5376) W (5376 x 256)) would run on a handful of CTAs: split K
+  int splits = 1;
+  const int tiles = grid.x * grid.y;
+  if (beta == 0.f && K >= 1024 && tiles < num_sms()) {
+    splits = 2 * num_sms() / tiles;
+    const int max_splits = K / 256;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  int k_chunk = (K + splits - 1) / splits;
+  k_chunk = (k_chunk + TK - 1) / TK * TK;
+  splits = (K + k_chunk - 1) / k_chunk;
+  grid.z = splits;
+  if (splits > 1) {
+    TEDM_CHECK(ldc == N, "sgemm: split-K needs a dense C");
+    TEDM_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, stream));
+  }
+  sgemm_kernel<<<grid, 256, 0, stream>>>(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, alpha, beta, k_chunk);
   TEDM_LAUNCH_CHECK();
   return 0;
 }

@@ -32,6 +32,17 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
+// Output row of parameter row `row`. For the qkv conv of CosineAttention the reference's channel order is
+// head*3*hd + d*3 + {q,k,v} (networks.py:194); the prepared operands use {q,k,v}*C + head*hd + d instead, so the
+// convolution itself emits de-interleaved q | k | v planes (a free re-layout: only weight rows move).
+__device__ __forceinline__ int out_row(const WeightDesc& d, int row) {
+  const int hd = d.qkv_head_dim;
+  if (hd == 0) return row;
+  const int head = row / (3 * hd), rem = row - head * 3 * hd;
+  const int dd = rem / 3, j = rem - dd * 3;
+  return j * (d.rows / 3) + head * hd + dd;
+}
+
 __device__ __forceinline__ int find_tensor(const WeightDesc* table, int n, int row) {
   int lo = 0, hi = n - 1;
   while (lo < hi) {
@@ -73,19 +84,20 @@ weight_prep_fwd_kernel(const WeightDesc* __restrict__ table, int n_tensors, int 
     stats[2 * row + 1] = norm;
   }
   const int taps = d.taps, cin = d.cin;
+  const int orow = out_row(d, row);
   for (int j = threadIdx.x; j < fan_in; j += kThreads) {
     float v = w[j] * s1;
     if (training) w[j] = v;
     const float wh = v * inv_s;
     const int ci = j / taps, tap = j - ci * taps;
     if (out_f32 != nullptr) out_f32[(size_t)row * fan_in + j] = wh;
-    if (out_fwd != nullptr) out_fwd[(size_t)row * d.kpad + tap * cin + ci] = __float2bfloat16_rn(wh);
+    if (out_fwd != nullptr) out_fwd[(size_t)orow * d.kpad + tap * cin + ci] = __float2bfloat16_rn(wh);
     if (out_dgrad != nullptr)
-      out_dgrad[((size_t)ci * taps + (taps - 1 - tap)) * d.rows + row] = __float2bfloat16_rn(wh);
+      out_dgrad[((size_t)ci * taps + (taps - 1 - tap)) * d.rows + orow] = __float2bfloat16_rn(wh);
   }
   if (out_fwd != nullptr) {
     for (int j = fan_in + threadIdx.x; j < d.kpad; j += kThreads)
-      out_fwd[(size_t)row * d.kpad + j] = __float2bfloat16_rn(0.f);
+      out_fwd[(size_t)orow * d.kpad + j] = __float2bfloat16_rn(0.f);
   }
 }
 
@@ -99,7 +111,7 @@ weight_prep_bwd_kernel(const WeightDesc* __restrict__ table, int n_tensors) {
   const int taps = d.taps, cin = d.cin;
   const int fan_in = cin * taps;
   const float* w = static_cast<const float*>(d.w) + (size_t)row * fan_in;
-  const float* g = static_cast<const float*>(d.g_hat) + (size_t)row * d.kpad;
+  const float* g = static_cast<const float*>(d.g_hat) + (size_t)out_row(d, row) * d.kpad;
   float* out = static_cast<float*>(d.grad) + (size_t)row * fan_in;
   const float* stats = static_cast<const float*>(d.stats);
   float dot = 0.f;

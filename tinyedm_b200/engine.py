@@ -61,6 +61,7 @@ class WeightSlot:
     ghat: Tensor | None = None  # fp32 [rows][kpad]  dL/dw_hat
     grad: Tensor | None = None  # fp32, shaped like the parameter
     row_start: int = 0
+    qkv_head_dim: int = 0       # != 0: rows permuted to the q | k | v plane layout (see tedm_weight_desc)
 
 
 class WeightBank:
@@ -157,6 +158,7 @@ class WeightBank:
             d.out_f32 = s.f32.data_ptr() if s.f32 is not None else None
             d.stats = self.stats.data_ptr() + 8 * s.row_start
             d.rows, d.cin, d.taps, d.kpad, d.row_start = s.rows, s.cin, s.taps, s.kpad, s.row_start
+            d.qkv_head_dim = s.qkv_head_dim
         raw = bytes(arr)
         host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
         self._table = host.to(self.device)
@@ -260,6 +262,7 @@ class DenoiserEngine:
                     bp.w[nm] = conv_slot(pre + nm + ".weight", mod.weight)
             if bp.attn:
                 bp.w["qkv"] = conv_slot(pre + "attention.qkv_conv.weight", blk.attention.qkv_conv.weight)
+                bp.w["qkv"].qkv_head_dim = bp.cout // m.num_heads
                 bp.w["out"] = conv_slot(pre + "attention.out_conv.weight", blk.attention.out_conv.weight)
             bp.w["embed"] = f32_slot(pre + "embed.weight", blk.embed.weight)
             bp.gain = blk.gain
@@ -440,10 +443,10 @@ class DenoiserEngine:
         if bp.attn:
             c5 = 1.0 / math.sqrt(2.0)
             qkv = ops.conv2d(out, bp.w["qkv"].fwd, 1, 3 * bp.cout)
-            y, qkvn, lse = ops.attention_forward(qkv, self.m.num_heads, need_lse=save)
+            y, lse = ops.attention_forward(qkv, self.m.num_heads, need_lse=save)
             out2 = ops.conv2d(y, bp.w["out"].fwd, 1, bp.cout, epi=EPI_AXPBY, alpha=c5, beta=c5, res=out)
             if save:
-                S.update(mid=out, qkv=qkv, qkvn=qkvn, lse=lse, y=y)
+                S.update(mid=out, qkv=qkv, lse=lse, y=y)
             out = out2
         return out, S
 
@@ -526,7 +529,7 @@ class DenoiserEngine:
         c5 = 1.0 / math.sqrt(2.0)
         g_y = ops.conv2d(g_out, bp.w["out"].dgrad, 1, bp.cout, alpha=c5)
         ops.conv2d_wgrad(g_out, S["y"], bp.w["out"].ghat, 1, alpha=c5)
-        g_qkv = ops.attention_backward(S["qkv"], S["qkvn"], S["y"], g_y, S["lse"], self.m.num_heads)
+        g_qkv = ops.attention_backward(S["qkv"], S["y"], g_y, S["lse"], self.m.num_heads)
         g_mid = ops.conv2d(g_qkv, bp.w["qkv"].dgrad, 1, bp.cout, epi=EPI_AXPBY, alpha=1.0, beta=c5, res=g_out)
         ops.conv2d_wgrad(g_qkv, S["mid"], bp.w["qkv"].ghat, 1)
         return g_mid

@@ -144,27 +144,26 @@ def channel_dot(A: Tensor, Bm: Tensor | None, out: Tensor, C: int, a_off: int, s
 # attention
 # ---------------------------------------------------------------------------------------------------------
 def attention_forward(qkv: Tensor, heads: int, need_lse: bool):
+    """qkv: (B,H,W,3C) with channel = {q,k,v}*C + head*hd + d. Returns (y, lse)."""
     B, H, W, C3 = qkv.shape
     C = C3 // 3
     hd = C // heads
     S = H * W
-    qkvn = torch.empty((3, B, heads, S, hd), device=qkv.device, dtype=BF16)
     y = torch.empty((B, H, W, C), device=qkv.device, dtype=BF16)
     lse = torch.empty((B * heads * S,), device=qkv.device, dtype=F32) if need_lse else None
-    _lib.call("tedm_attention_forward", qkv.data_ptr(), qkvn.data_ptr(), y.data_ptr(), _p(lse), B, S, heads, hd, _stream())
-    return y, qkvn, lse
+    _lib.call("tedm_attention_forward", qkv.data_ptr(), y.data_ptr(), _p(lse), B, S, heads, hd, _stream())
+    return y, lse
 
 
-def attention_backward(qkv: Tensor, qkvn: Tensor, y: Tensor, g_y: Tensor, lse: Tensor, heads: int) -> Tensor:
+def attention_backward(qkv: Tensor, y: Tensor, g_y: Tensor, lse: Tensor, heads: int) -> Tensor:
     B, H, W, C3 = qkv.shape
     C = C3 // 3
     hd = C // heads
     S = H * W
     delta = torch.empty_like(lse)
-    g_qkvn = torch.empty_like(qkvn)
     g_qkv = torch.empty_like(qkv)
-    _lib.call("tedm_attention_backward", qkv.data_ptr(), qkvn.data_ptr(), y.data_ptr(), g_y.data_ptr(), lse.data_ptr(),
-              delta.data_ptr(), g_qkvn.data_ptr(), g_qkv.data_ptr(), B, S, heads, hd, _stream())
+    _lib.call("tedm_attention_backward", qkv.data_ptr(), y.data_ptr(), g_y.data_ptr(), lse.data_ptr(), delta.data_ptr(),
+              g_qkv.data_ptr(), B, S, heads, hd, _stream())
     return g_qkv
 
 
