@@ -65,14 +65,17 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
-    def stop(self) -> dict:
+    def mark(self) -> int:
+        """Index of the next sample: call at both ends of the timed region."""
+        return len(self.lines)
+
+    def stop(self, first: int = 0, last: int | None = None) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[first:last]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -246,14 +249,20 @@ def run_b200(args) -> None:
         barrier()
         return max_over_ranks(e0.elapsed_time(e1))
 
+    clocks = ClockSampler(local)
+    clocks.start()                      # nvidia-smi needs a few hundred ms to produce its first sample: start early
     for i in range(args.warmup):
         train_step((dev_imgs[i % n_pool], dev_lbls[i % n_pool]))
-    clocks = ClockSampler(local)
-    clocks.start()
+    torch.cuda.synchronize()
+    t_wait = time.time()
+    while clocks.mark() == 0 and time.time() - t_wait < 3.0:
+        time.sleep(0.05)
+    c0 = clocks.mark()
     with LaunchCounter(_lib) as lc:
         ms_dev = timed(lambda i: train_step((dev_imgs[i % n_pool], dev_lbls[i % n_pool])), args.steps)
     launches = lc.n
-    clk = clocks.stop()
+    time.sleep(0.12)                    # let the sample that covers the end of the region arrive
+    c1 = clocks.mark()
 
     def e2e_step(i):
         x = host_imgs[i % n_pool].to(dev, non_blocking=True)
@@ -261,6 +270,7 @@ def run_b200(args) -> None:
         loss = train_step((x, y))
         loss_host[i].copy_(loss.detach(), non_blocking=True)
     ms_e2e = timed(e2e_step, args.steps)
+    clk = clocks.stop(c0, max(c1, c0 + 1))
     final_loss = float(loss_host[args.steps - 1])
     value = world * B * args.steps / (ms_dev / 1e3)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
@@ -376,7 +386,7 @@ TRAFFIC_BYTES = None
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=TRAIN_BATCH, help="per-GPU training batch (the metric is quoted on 256)")
