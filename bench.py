@@ -282,6 +282,7 @@ def run_b200(args) -> None:
     ydom = torch.empty(DOM["B"], DOM["H"], DOM["W"], DOM["Cout"], device=dev, dtype=torch.bfloat16)
     dom_events = []
     orig_conv = ops.conv2d
+    flavour = {0: "plain", 1: "fwd+modulation*silu*dropout", 2: "fwd+mp_add", 3: "dgrad+modsilu adjoint", 4: "dgrad+silu/pixelnorm adjoint"}
 
     def conv_probe(x, w, ksize, cout, **kw):
         if ksize == 3 and tuple(x.shape) == (DOM["B"], DOM["H"], DOM["W"], DOM["Cin"]) and cout == DOM["Cout"]:
@@ -289,7 +290,7 @@ def run_b200(args) -> None:
             a.record()
             out = orig_conv(x, w, ksize, cout, **kw)
             b.record()
-            dom_events.append((a, b))
+            dom_events.append((a, b, kw.get("epi", 0)))
             return out
         return orig_conv(x, w, ksize, cout, **kw)
     import tinyedm_b200.engine as engine_mod
@@ -304,15 +305,22 @@ def run_b200(args) -> None:
     finally:
         engine_mod.ops.conv2d = orig_conv
     torch.cuda.synchronize()
-    dom_ms = sorted(a.elapsed_time(b) for a, b in dom_events)
+    dom_ms = [a.elapsed_time(b) for a, b, _ in dom_events]
     dom_avg = sum(dom_ms) / len(dom_ms)
     pk = peaks()
     peak_tf = pk.get("bf16_tflops_sustained") or 1400.0
     achieved_tf = DOM_FLOP / (dom_avg * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel<256> 3x3 256->256 @32x32 B256 (fwd + dgrad launches)",
+    by_epi = {}
+    for (a, b, e) in dom_events:
+        by_epi.setdefault(e, []).append(a.elapsed_time(b))
+    per_flavour = {flavour.get(e, str(e)): {"launches": len(v), "ms_avg": sum(v) / len(v),
+                                            "tflops": DOM_FLOP / (sum(v) / len(v) * 1e-3) / 1e12} for e, v in sorted(by_epi.items())}
+    roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel<256,*> 3x3 256->256 @32x32 B256, every launch of this shape in a "
+                "training step (forward and data-gradient, with their fused epilogues)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if pk else "fallback (B200_PROFILING.md)",
-                "launch_ms_avg": dom_avg, "launches_timed": len(dom_ms), "traffic": TRAFFIC_BYTES}
+                "launch_ms_avg": dom_avg, "launches_timed": len(dom_ms), "traffic": TRAFFIC_BYTES,
+                "per_epilogue": per_flavour}
 
     # ---------------- sampling (configs[2]) ----------------
     del opt

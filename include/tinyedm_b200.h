@@ -55,11 +55,17 @@ int tedm_weight_prep_backward(const tedm_weight_desc* table, int n, int total_ro
  *             Philox stream keyed by seed (+ *seed_ptr, an optional DEVICE step counter so that a captured CUDA graph
  *             draws a fresh mask on every replay)
  *           2 axpby: out = alpha*conv + beta*res; mp_add(x, conv, t) is alpha = t/c, beta = (1-t)/c,
- *             c = sqrt((1-t)^2+t^2)                                                     (networks.py:87-88, :263, :327) */
+ *             c = sqrt((1-t)^2+t^2)                                                     (networks.py:87-88, :263, :327)
+ *         Backward epilogues (the call is then the DATA GRADIENT of a conv, `conv` = alpha * dgrad):
+ *           3 adjoint of epilogue 1 fused into the dgrad of conv_3x3_2: conv = dL/dh; out = dL/draw;
+ *             d_mod[b,c] += sum_pixels (needs aux = raw, mod, d_mod zeroed by the caller, the same seed/seed_ptr)
+ *           4 adjoint of a = mp_silu(x) fused into the dgrad of conv_3x3_1: out = conv*mp_silu'(aux=x) + beta*res,
+ *             then, when nrm (eps + rms per pixel, from tedm_block_prep_forward) is given, the pixel_norm adjoint
+ *             g/n - x*sum_c(g*x)/((n-eps)*C) (needs Cout <= 256), then out += previous out when accumulate_out   */
 int tedm_conv2d_forward(const void* x, const void* w, void* out, int B, int H, int W, int Cin, int Cout, int ksize,
                         int epilogue, float alpha, void* raw, const void* res, float beta, const float* mod,
                         int mod_stride, float drop_p, uint64_t seed, const uint64_t* seed_ptr, int block_n,
-                        tedm_stream_t stream);
+                        const void* aux, float* d_mod, const float* nrm, int accumulate_out, tedm_stream_t stream);
 /* dL/dw_hat of the convolution above: dw[co][tap][ci] (=|+=) alpha * sum_p g[p,co] * x[p+tap,ci]  (autograd of :37) */
 int tedm_conv2d_wgrad(const void* g, const void* x, float* dw, int B, int H, int W, int Cin, int Cout, int ksize,
                       float alpha, int accumulate, int splits, tedm_stream_t stream);

@@ -24,7 +24,7 @@ int tedm_init(int device) {
 int tedm_conv2d_forward(const void* x, const void* w, void* out, int B, int H, int W, int Cin, int Cout, int ksize,
                         int epilogue, float alpha, void* raw, const void* res, float beta, const float* mod,
                         int mod_stride, float drop_p, uint64_t seed, const uint64_t* seed_ptr, int block_n,
-                        tedm_stream_t stream) {
+                        const void* aux, float* d_mod, const float* nrm, int accumulate_out, tedm_stream_t stream) {
   ConvGemmArgs a{};
   a.x = static_cast<const __nv_bfloat16*>(x);
   a.w = static_cast<const __nv_bfloat16*>(w);
@@ -37,6 +37,8 @@ int tedm_conv2d_forward(const void* x, const void* w, void* out, int B, int H, i
   a.mod = mod; a.mod_stride = mod_stride; a.drop_p = drop_p; a.seed = seed;
   a.seed_ptr = reinterpret_cast<const unsigned long long*>(seed_ptr);
   a.block_n_override = block_n;
+  a.aux = static_cast<const __nv_bfloat16*>(aux);
+  a.d_mod = d_mod; a.nrm = nrm; a.accumulate_out = accumulate_out;
   return conv_gemm_launch(a, static_cast<cudaStream_t>(stream));
 }
 

@@ -258,6 +258,21 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t k
   return make_uint4(c0, c1, c2, c3);
 }
 
+// Dropout RNG: counter-based, stateless, cheap enough for a GEMM epilogue. One avalanche hash (lowbias32) per PAIR of
+// consecutive channels yields two 16-bit uniforms; element e is kept iff its 16 bits >= p * 65536. Forward and backward
+// regenerate the same bits from (element index, seed), so no mask is ever stored.
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t dropout_seed(uint32_t seed_lo, uint32_t seed_hi) {
+  return hash32(seed_lo ^ hash32(seed_hi + 0x9E3779B9u));
+}
+// e: even element index; returns bits for elements e (low 16) and e+1 (high 16)
+__device__ __forceinline__ uint32_t dropout_bits2(unsigned long long e, uint32_t seed) {
+  return hash32(((uint32_t)(e >> 1) + (uint32_t)(e >> 33) * 0x85EBCA6Bu) ^ seed);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -23,7 +23,8 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;          // 64 bf16 = one 128-byte swizzle row
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
-constexpr int kNumThreads = 256;
+constexpr int kNumThreads = 384;     // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue (2 per TMEM lane quarter)
+constexpr int kEpiWarps = 8;
 
 template <int BN>
 struct GemmCfg {
@@ -31,7 +32,7 @@ struct GemmCfg {
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*row dots*/;
 };
 
 struct Tile {
@@ -58,7 +59,74 @@ __device__ __forceinline__ Tile decode_tile(const ConvGemmParams& p, int tile) {
   return t;
 }
 
-template <int BN>
+// 32 values per lane -> lane j ends up with the sum over all 32 lanes of value j (31 shuffles, no shared memory).
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+// pulls `bytes` of a row into L2 (issued one tile ahead of its use)
+__device__ __forceinline__ void prefetch_row_l2(const void* ptr, int bytes) {
+  const char* c = static_cast<const char*>(ptr);
+  for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + o));
+}
+
+template <int CW>
+__device__ __forceinline__ void row_load(const __nv_bfloat16* src, float (&f)[CW]) {
+#pragma unroll
+  for (int g = 0; g < CW / 8; ++g) {
+    const uint4 u = *reinterpret_cast<const uint4*>(src + g * 8);
+    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+    f[g * 8 + 0] = a.x; f[g * 8 + 1] = a.y; f[g * 8 + 2] = b.x; f[g * 8 + 3] = b.y;
+    f[g * 8 + 4] = c.x; f[g * 8 + 5] = c.y; f[g * 8 + 6] = d.x; f[g * 8 + 7] = d.y;
+  }
+}
+
+template <int CW>
+__device__ __forceinline__ void row_store(__nv_bfloat16* dst, const float (&v)[CW], int n_valid) {
+#pragma unroll
+  for (int g = 0; g < CW / 8; ++g) {
+    if (g * 8 < n_valid) {
+      uint4 o;
+      o.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+      o.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+      o.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+      o.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+      *reinterpret_cast<uint4*>(dst + g * 8) = o;
+    }
+  }
+}
+
+template <int CW>
+__device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t (&r)[CW]);
+template <>
+__device__ __forceinline__ void tmem_ld_cw<32>(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_ld_cw<16>(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
+
+// v[i] *= keep(e0 + i) / (1 - p) for the CW consecutive elements starting at the even element index e0
+template <int CW>
+__device__ __forceinline__ void dropout_apply(float (&v)[CW], unsigned long long e0, float drop_p, uint32_t dseed) {
+  const float keep_scale = 1.0f / (1.0f - drop_p);
+  const uint32_t thresh = (uint32_t)(drop_p * 65536.0f);
+#pragma unroll
+  for (int i = 0; i < CW; i += 2) {
+    const uint32_t bits = dropout_bits2(e0 + i, dseed);
+    v[i] = (bits & 0xFFFFu) >= thresh ? v[i] * keep_scale : 0.f;
+    v[i + 1] = (bits >> 16) >= thresh ? v[i + 1] * keep_scale : 0.f;
+  }
+}
+
+template <int BN, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const ConvGemmParams p) {
@@ -87,7 +155,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], kEpiWarps);  // one arrive per epilogue warp
     }
     mbar_fence_init();
   }
@@ -161,8 +229,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
+    // ===================== epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =====================
+    constexpr int CW = (EPI == EPI_SILU_BWD) ? 16 : 32;   // columns per step (register budget of the heavy adjoint)
     const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2; // which half of the tile's columns this warp owns
     const int m = q * 32 + lane;      // accumulator row == pixel within the tile
     const int rows_in_tile = p.NB * p.RH * p.W;
     const int HW = p.H * p.W;
@@ -171,110 +241,177 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // dropout seed = per-launch salt + a device-resident step counter (fresh masks under CUDA-graph replay)
     unsigned long long seed64 = ((unsigned long long)p.seed_hi << 32) | p.seed_lo;
     if (p.seed_ptr != nullptr) seed64 += *p.seed_ptr * 0x9E3779B97F4A7C15ull;
-    const uint32_t seed_lo = (uint32_t)seed64, seed_hi = (uint32_t)(seed64 >> 32);
+    const uint32_t dseed = dropout_seed((uint32_t)seed64, (uint32_t)(seed64 >> 32));
+    // a warp's 32 rows belong to ONE image when tiles never mix images or images are a multiple of 32 pixels
+    const bool warp_one_image = (p.NB == 1) || (HW % 32 == 0);
+    constexpr bool kNeedAux = (EPI == EPI_MODSILU_BWD || EPI == EPI_SILU_BWD);
+    constexpr bool kMayRes = (EPI == EPI_AXPBY || EPI == EPI_SILU_BWD);
+    const bool use_res = kMayRes && p.res != nullptr;
+    const bool use_old = (EPI == EPI_SILU_BWD) && p.accumulate_out;
+    float* row_dots = reinterpret_cast<float*>(tmem_ptr + 4);   // [2 parities][2 halves][128 rows]
+    int parity = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       Tile t = decode_tile(p, tile);
       int n_this = p.Cout - t.n0;
       if (n_this > BN) n_this = BN;
+      // column range of this warp: [cb, ce)
+      int cs = ((n_this / 2 + 31) / 32) * 32;
+      if (cs > n_this) cs = n_this;
+      const int cb = half == 0 ? 0 : cs, ce = half == 0 ? cs : n_this;
       const long long pix = t.p_base + m;
       const bool valid = (m < rows_in_tile) && (pix < t.p_limit);
       const int b = valid ? (int)(pix / HW) : 0;
+      const long long row_off = pix * p.Cout + t.n0;
+      __nv_bfloat16* out_row = p.out + row_off;
+      // epilogue operands live in HBM: start the NEXT tile's rows towards L2 now (a whole tile of lead time)
+      if ((kNeedAux || use_res || use_old) && tile + (int)gridDim.x < total_tiles) {
+        const Tile tn = decode_tile(p, tile + gridDim.x);
+        const long long pn = tn.p_base + m;
+        if (m < rows_in_tile && pn < tn.p_limit) {
+          int nn = p.Cout - tn.n0;
+          if (nn > BN) nn = BN;
+          int csn = ((nn / 2 + 31) / 32) * 32;
+          if (csn > nn) csn = nn;
+          const int cbn = half == 0 ? 0 : csn, cen = half == 0 ? csn : nn;
+          const long long off = pn * p.Cout + tn.n0 + cbn;
+          if (cen > cbn) {
+            if (kNeedAux) prefetch_row_l2(p.aux + off, (cen - cbn) * 2);
+            if (use_res) prefetch_row_l2(p.res + off, (cen - cbn) * 2);
+            if (use_old) prefetch_row_l2(p.out + off, (cen - cbn) * 2);
+          }
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      __nv_bfloat16* out_row = p.out + pix * p.Cout + t.n0;
-      for (int c0 = 0; c0 < n_this; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(t_row + c0, r);
+
+      float inv_n = 1.0f, kk = 0.f;
+      if constexpr (EPI == EPI_SILU_BWD) if (p.nrm != nullptr) {
+        // sweep 1 of the fused pixel-norm adjoint: dot = sum_c v*x with v = alpha*acc*silu'(x) + beta*res; the two
+        // column halves of a row live in two warps: partial dots are exchanged through shared memory
+        float dot = 0.f;
+        for (int c0 = cb; c0 < ce; c0 += CW) {
+          uint32_t r[CW];
+          tmem_ld_cw<CW>(t_row + c0, r);
+          tmem_ld_wait();
+          if (valid) {
+            float xv[CW], rv[CW];
+            row_load<CW>(p.aux + row_off + c0, xv);
+            if (use_res) row_load<CW>(p.res + row_off + c0, rv);
+#pragma unroll
+            for (int i = 0; i < CW; ++i) {
+              float v = __uint_as_float(r[i]) * p.alpha * mp_silu_grad_f(xv[i]);
+              if (use_res) v += p.beta * rv[i];
+              dot += v * xv[i];
+            }
+          }
+        }
+        float* slot = row_dots + parity * 256;
+        slot[half * 128 + m] = dot;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // the two warps sharing this lane quarter
+        dot = slot[m] + slot[128 + m];
+        const float n = valid ? p.nrm[pix] : 1.0f;
+        inv_n = 1.0f / n;
+        kk = dot / (fmaxf(n - 1e-4f, 1e-20f) * (float)p.Cout);
+      }
+      for (int c0 = cb; c0 < ce; c0 += CW) {
+        uint32_t r[CW];
+        tmem_ld_cw<CW>(t_row + c0, r);
         tmem_ld_wait();
-        if (valid) {
-          float v[32];
+        float v[CW];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-          if (p.epi == EPI_MODSILU) {
+        for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+        if constexpr (EPI == EPI_MODSILU_BWD) {
+          // backward of h = drop(mp_silu(raw * m)) fused into the data gradient of the next conv:
+          //   gz = g_h * keep/(1-p) * mp_silu'(raw*m);  g_raw = gz * m;  d_mod[b,c] += sum_pixels gz * raw
+          float dm[CW];
+          if (valid) {
+            float rw[CW];
+            row_load<CW>(p.aux + row_off + c0, rw);
             const float* mrow = p.mod + (long long)b * p.mod_stride + t.n0 + c0;
-            if (p.out2 != nullptr) {
-              __nv_bfloat16* raw_row = p.out2 + pix * p.Cout + t.n0 + c0;
+            if (p.drop_p > 0.f) dropout_apply<CW>(v, (unsigned long long)pix * p.Cout + t.n0 + c0, p.drop_p, dseed);
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                if (c0 + g * 8 < n_this) {
-                  uint4 o;
-                  o.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
-                  o.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-                  o.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
-                  o.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-                  *reinterpret_cast<uint4*>(raw_row + g * 8) = o;
-                }
+            for (int g = 0; g < CW / 4; ++g) {
+              const float4 mm = *reinterpret_cast<const float4*>(mrow + g * 4);
+              const float mv[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int i = g * 4 + j;
+                const float gz = v[i] * mp_silu_grad_f(rw[i] * mv[j]);
+                v[i] = gz * mv[j];
+                dm[i] = gz * rw[i];
               }
             }
+          } else {
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
+            for (int i = 0; i < CW; ++i) dm[i] = 0.f;
+          }
+          if (warp_one_image) {
+            const long long pw = t.p_base + q * 32;          // first pixel of this warp's rows
+            const float tot = warp_transpose_reduce(dm, lane);
+            if (q * 32 < rows_in_tile && pw < t.p_limit && c0 + lane < n_this)
+              atomicAdd(p.d_mod + (long long)(pw / HW) * p.mod_stride + t.n0 + c0 + lane, tot);
+          } else if (valid) {
+#pragma unroll
+            for (int i = 0; i < CW; ++i)
+              if (c0 + i < n_this) atomicAdd(p.d_mod + (long long)b * p.mod_stride + t.n0 + c0 + i, dm[i]);
+          }
+        }
+        if (valid) {
+          if constexpr (EPI == EPI_MODSILU) {
+            const float* mrow = p.mod + (long long)b * p.mod_stride + t.n0 + c0;
+            // the reference's conv output is bf16 before the fp32 modulation island (networks.py:253-258);
+            // the stored (bf16) pre-modulation value is also what backward sees
+#pragma unroll
+            for (int i = 0; i < CW; ++i) v[i] = bf16_round(v[i]);
+            if (p.out2 != nullptr) row_store<CW>(p.out2 + row_off + c0, v, n_this - c0);
+#pragma unroll
+            for (int g = 0; g < CW / 4; ++g) {
               if (c0 + g * 4 < n_this) {
-                float4 mm = *reinterpret_cast<const float4*>(mrow + g * 4);
-                // the reference's conv output is bf16 before the fp32 modulation island (networks.py:253-258);
-                // the stored (bf16) pre-modulation value is also what backward sees
-                float r0 = bf16_round(v[g * 4 + 0]);
-                float r1 = bf16_round(v[g * 4 + 1]);
-                float r2 = bf16_round(v[g * 4 + 2]);
-                float r3 = bf16_round(v[g * 4 + 3]);
-                v[g * 4 + 0] = mp_silu_f(r0 * mm.x);
-                v[g * 4 + 1] = mp_silu_f(r1 * mm.y);
-                v[g * 4 + 2] = mp_silu_f(r2 * mm.z);
-                v[g * 4 + 3] = mp_silu_f(r3 * mm.w);
+                const float4 mm = *reinterpret_cast<const float4*>(mrow + g * 4);
+                v[g * 4 + 0] = mp_silu_f(v[g * 4 + 0] * mm.x);
+                v[g * 4 + 1] = mp_silu_f(v[g * 4 + 1] * mm.y);
+                v[g * 4 + 2] = mp_silu_f(v[g * 4 + 2] * mm.z);
+                v[g * 4 + 3] = mp_silu_f(v[g * 4 + 3] * mm.w);
               }
             }
-            if (p.drop_p > 0.f) {
-              const float keep_scale = 1.0f / (1.0f - p.drop_p);
-              const uint32_t thresh = (uint32_t)(p.drop_p * 4294967296.0);
-              const unsigned long long e0 = (unsigned long long)pix * p.Cout + t.n0 + c0;
-              const uint32_t s_lo = seed_lo, s_hi = seed_hi;
+            if (p.drop_p > 0.f) dropout_apply<CW>(v, (unsigned long long)pix * p.Cout + t.n0 + c0, p.drop_p, dseed);
+          } else if constexpr (EPI == EPI_AXPBY) {
+            float rv[CW];
+            row_load<CW>(p.res + row_off + c0, rv);
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                unsigned long long ctr = (e0 >> 2) + g;  // one Philox call per 4 consecutive channels
-                uint4 rnd = philox4x32((uint32_t)ctr, (uint32_t)(ctr >> 32), s_lo, s_hi);
-                v[g * 4 + 0] = rnd.x >= thresh ? v[g * 4 + 0] * keep_scale : 0.f;
-                v[g * 4 + 1] = rnd.y >= thresh ? v[g * 4 + 1] * keep_scale : 0.f;
-                v[g * 4 + 2] = rnd.z >= thresh ? v[g * 4 + 2] * keep_scale : 0.f;
-                v[g * 4 + 3] = rnd.w >= thresh ? v[g * 4 + 3] * keep_scale : 0.f;
-              }
+            for (int i = 0; i < CW; ++i) v[i] += p.beta * rv[i];
+          } else if constexpr (EPI == EPI_SILU_BWD) {
+            // g_x = alpha*acc * mp_silu'(x) + beta*res, [pixel-norm adjoint], (+ what is already in `out`)
+            float xv[CW];
+            row_load<CW>(p.aux + row_off + c0, xv);
+#pragma unroll
+            for (int i = 0; i < CW; ++i) v[i] *= mp_silu_grad_f(xv[i]);
+            if (use_res) {
+              float rv[CW];
+              row_load<CW>(p.res + row_off + c0, rv);
+#pragma unroll
+              for (int i = 0; i < CW; ++i) v[i] += p.beta * rv[i];
             }
-          } else if (p.epi == EPI_AXPBY) {
-            const __nv_bfloat16* res_row = p.res + pix * p.Cout + t.n0 + c0;
-            const float wa = p.beta, wb = 1.0f;  // alpha already applied to v[]
+            if (p.nrm != nullptr) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (c0 + g * 8 < n_this) {
-                uint4 rr = *reinterpret_cast<const uint4*>(res_row + g * 8);
-                float2 f0 = unpack_bf16(rr.x), f1 = unpack_bf16(rr.y), f2 = unpack_bf16(rr.z),
-                       f3 = unpack_bf16(rr.w);
-                v[g * 8 + 0] = wa * f0.x + wb * v[g * 8 + 0];
-                v[g * 8 + 1] = wa * f0.y + wb * v[g * 8 + 1];
-                v[g * 8 + 2] = wa * f1.x + wb * v[g * 8 + 2];
-                v[g * 8 + 3] = wa * f1.y + wb * v[g * 8 + 3];
-                v[g * 8 + 4] = wa * f2.x + wb * v[g * 8 + 4];
-                v[g * 8 + 5] = wa * f2.y + wb * v[g * 8 + 5];
-                v[g * 8 + 6] = wa * f3.x + wb * v[g * 8 + 6];
-                v[g * 8 + 7] = wa * f3.y + wb * v[g * 8 + 7];
-              }
+              for (int i = 0; i < CW; ++i) v[i] = v[i] * inv_n - xv[i] * kk;
+            }
+            if (use_old) {
+              float ov[CW];
+              row_load<CW>(out_row + c0, ov);
+#pragma unroll
+              for (int i = 0; i < CW; ++i) v[i] += ov[i];
             }
           }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (c0 + g * 8 < n_this) {
-              uint4 o;
-              o.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
-              o.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-              o.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
-              o.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-              *reinterpret_cast<uint4*>(out_row + c0 + g * 8) = o;
-            }
-          }
+          row_store<CW>(out_row + c0, v, n_this - c0);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      parity ^= 1;
     }
   }
 
@@ -286,20 +423,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
-template <int BN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvGemmParams& p, cudaStream_t stream) {
+template <int BN, int EPI>
+int launch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const ConvGemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    TEDM_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TEDM_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::kSmemBytes));
     configured = true;
   }
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
-  conv_gemm_kernel<BN><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  conv_gemm_kernel<BN, EPI><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   TEDM_LAUNCH_CHECK();
   return 0;
+}
+
+template <int BN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvGemmParams& p, cudaStream_t stream) {
+  switch (p.epi) {
+    case EPI_PLAIN: return launch_epi<BN, EPI_PLAIN>(ta, tb, p, stream);
+    case EPI_MODSILU: return launch_epi<BN, EPI_MODSILU>(ta, tb, p, stream);
+    case EPI_AXPBY: return launch_epi<BN, EPI_AXPBY>(ta, tb, p, stream);
+    case EPI_MODSILU_BWD: return launch_epi<BN, EPI_MODSILU_BWD>(ta, tb, p, stream);
+    case EPI_SILU_BWD: return launch_epi<BN, EPI_SILU_BWD>(ta, tb, p, stream);
+    default: return fail("conv_gemm: unknown epilogue %d", p.epi);
+  }
 }
 
 }  // namespace
@@ -341,8 +490,17 @@ int conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t stream) {
   p.epi = a.epi; p.alpha = a.alpha; p.out = a.out; p.out2 = a.out2; p.res = a.res;
   p.beta = a.beta; p.mod = a.mod; p.mod_stride = a.mod_stride;
   p.drop_p = a.drop_p; p.seed_lo = (uint32_t)a.seed; p.seed_hi = (uint32_t)(a.seed >> 32); p.seed_ptr = a.seed_ptr;
+  p.aux = a.aux; p.d_mod = a.d_mod; p.nrm = a.nrm; p.accumulate_out = a.accumulate_out;
   if (a.epi == EPI_MODSILU) TEDM_CHECK(a.mod != nullptr, "conv_gemm: MODSILU epilogue needs mod");
   if (a.epi == EPI_AXPBY) TEDM_CHECK(a.res != nullptr, "conv_gemm: AXPBY epilogue needs res");
+  if (a.epi == EPI_MODSILU_BWD)
+    TEDM_CHECK(a.mod != nullptr && a.aux != nullptr && a.d_mod != nullptr, "conv_gemm: MODSILU_BWD epilogue needs mod, raw and d_mod");
+  if (a.epi == EPI_SILU_BWD) {
+    TEDM_CHECK(a.aux != nullptr, "conv_gemm: SILU_BWD epilogue needs x");
+    TEDM_CHECK(a.nrm == nullptr || a.Cout <= 256, "conv_gemm: fused pixel-norm adjoint needs Cout <= 256 (one N tile)");
+  }
+  TEDM_CHECK(a.Cout % 32 == 0 || a.epi == EPI_PLAIN || a.epi == EPI_AXPBY || a.epi == EPI_MODSILU,
+             "conv_gemm: backward epilogues need Cout %% 32 == 0");
 
   CUtensorMap ta, tb;
   {

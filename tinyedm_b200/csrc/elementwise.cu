@@ -298,26 +298,21 @@ modsilu_bwd_kernel(const ModSiluBwdArgs a) {
   if (rr < rows) {
     const Vec8 m = load8f(a.mod + (long long)b * a.mod_stride + v * 8);
     const float keep_scale = a.drop_p > 0.f ? 1.0f / (1.0f - a.drop_p) : 1.0f;
-    const uint32_t thresh = (uint32_t)(a.drop_p * 4294967296.0);
+    const uint32_t thresh = (uint32_t)(a.drop_p * 65536.0f);
     unsigned long long seed64 = ((unsigned long long)a.seed_hi << 32) | a.seed_lo;
     if (a.seed_ptr != nullptr) seed64 += *a.seed_ptr * 0x9E3779B97F4A7C15ull;
-    const uint32_t seed_lo = (uint32_t)seed64, seed_hi = (uint32_t)(seed64 >> 32);
+    const uint32_t dseed = dropout_seed((uint32_t)seed64, (uint32_t)(seed64 >> 32));
     for (int p = p_begin + rr; p < p_end; p += rows) {
       const long long o = ((long long)b * a.HW + p) * a.C + v * 8;
       Vec8 g = load8(a.g_h + o);
       const Vec8 r = load8(a.raw + o);
       if (a.drop_p > 0.f) {
-        const unsigned long long ctr = (unsigned long long)o >> 2;
-        uint4 r0 = philox4x32((uint32_t)ctr, (uint32_t)(ctr >> 32), seed_lo, seed_hi);
-        uint4 r1 = philox4x32((uint32_t)(ctr + 1), (uint32_t)((ctr + 1) >> 32), seed_lo, seed_hi);
-        g.v[0] = r0.x >= thresh ? g.v[0] * keep_scale : 0.f;
-        g.v[1] = r0.y >= thresh ? g.v[1] * keep_scale : 0.f;
-        g.v[2] = r0.z >= thresh ? g.v[2] * keep_scale : 0.f;
-        g.v[3] = r0.w >= thresh ? g.v[3] * keep_scale : 0.f;
-        g.v[4] = r1.x >= thresh ? g.v[4] * keep_scale : 0.f;
-        g.v[5] = r1.y >= thresh ? g.v[5] * keep_scale : 0.f;
-        g.v[6] = r1.z >= thresh ? g.v[6] * keep_scale : 0.f;
-        g.v[7] = r1.w >= thresh ? g.v[7] * keep_scale : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          const uint32_t bits = dropout_bits2((unsigned long long)o + i, dseed);
+          g.v[i] = (bits & 0xFFFFu) >= thresh ? g.v[i] * keep_scale : 0.f;
+          g.v[i + 1] = (bits >> 16) >= thresh ? g.v[i + 1] * keep_scale : 0.f;
+        }
       }
       Vec8 out;
 #pragma unroll

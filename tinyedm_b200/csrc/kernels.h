@@ -18,6 +18,9 @@ enum ConvEpilogue : int {
   EPI_PLAIN = 0,    // out = alpha * acc
   EPI_MODSILU = 1,  // out = dropout(mp_silu(acc * mod[b, c])); optional raw copy of acc in out2
   EPI_AXPBY = 2,    // out = alpha * acc + beta * res   (mp_add, networks.py:87-88: alpha = t/c, beta = (1-t)/c)
+  EPI_MODSILU_BWD = 3,  // acc = dL/dh of h = drop(mp_silu(raw*mod)): out = dL/draw, d_mod[b,c] += sum_pix (autograd of :255-261)
+  EPI_SILU_BWD = 4,     // acc = dL/da of a = mp_silu(x): out = alpha*acc*mp_silu'(x) + beta*res, optional pixel-norm adjoint
+                        // (given nrm) and accumulation into out (autograd of :249-252, :263)
 };
 
 struct ConvGemmArgs {
@@ -36,6 +39,10 @@ struct ConvGemmArgs {
   uint64_t seed;
   const unsigned long long* seed_ptr;  // optional device step counter mixed into the seed
   int block_n_override;      // 0 = heuristic
+  const __nv_bfloat16* aux;  // MODSILU_BWD: raw conv output; SILU_BWD: x          (B,H,W,Cout)
+  float* d_mod;              // MODSILU_BWD: (B, mod_stride) fp32, column offset applied, accumulated atomically
+  const float* nrm;          // SILU_BWD: (B*H*W) eps + rms of the pixel norm whose adjoint is fused, or null
+  int accumulate_out;        // SILU_BWD: out += result
 };
 
 // Device-side parameter block of the implicit-GEMM kernel.
@@ -53,6 +60,10 @@ struct ConvGemmParams {
   float drop_p;
   uint32_t seed_lo, seed_hi;
   const unsigned long long* seed_ptr;
+  const __nv_bfloat16* aux;
+  float* d_mod;
+  const float* nrm;
+  int accumulate_out;
 };
 
 int conv_tile_geometry(int H, int W, int* RH, int* NB);

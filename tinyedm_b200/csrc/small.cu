@@ -540,9 +540,9 @@ int sgemm(const float* A, const float* B, float* C, int M, int N, int K, int lda
   // long-K, few-tile problems (e.g. g_emb = d_lin (B x 5376) W (5376 x 256)) would run on a handful of CTAs: split K
   int splits = 1;
   const int tiles = grid.x * grid.y;
-  if (beta == 0.f && K >= 1024 && tiles < num_sms()) {
+  if (beta == 0.f && ((K >= 1024 && tiles < num_sms()) || (K >= 128 && tiles <= 8))) {
     splits = 2 * num_sms() / tiles;
-    const int max_splits = K / 256;
+    const int max_splits = K >= 1024 ? K / 256 : K / 32;   // tiny problems are latency bound: 2 k-steps per CTA
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
   }

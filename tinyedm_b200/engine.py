@@ -31,7 +31,8 @@ import torch
 from torch import Tensor
 
 from . import _lib, ops
-from .ops import BF16, F32, EPI_AXPBY, EPI_MODSILU, RESAMPLE_DOWN, RESAMPLE_NONE, RESAMPLE_UP
+from .ops import (BF16, F32, EPI_AXPBY, EPI_MODSILU, EPI_MODSILU_BWD, EPI_SILU_BWD, RESAMPLE_DOWN, RESAMPLE_NONE,
+                  RESAMPLE_UP)
 
 _ALIGN = 128  # elements; keeps every slice of the flat buffers 256-byte aligned for TMA
 
@@ -131,6 +132,19 @@ class WeightBank:
         self._have_grad_buffers = True
         self._table = None
 
+    def begin_backward(self) -> None:
+        """Call before a backward writes into the gradient buffers. `param.grad` tensors handed out by an earlier
+        backward are views of the current buffer; if any is still alive (gradient accumulation without zero_grad), the
+        bank moves to a fresh buffer instead of overwriting them."""
+        self.ensure_grad_buffers()
+        if any(s.param.grad is not None for s in self.slots):
+            self.fresh_grad_buffer()
+
+    def autograd_grads(self) -> list[Tensor]:
+        """One NEW view object per slot (sole owner -> autograd's AccumulateGrad adopts it instead of cloning; the
+        underlying pointers stay the same from step to step, so the optimiser's descriptor table stays valid)."""
+        return [s.grad.view(s.grad.shape) for s in self.slots]
+
     def fresh_grad_buffer(self) -> None:
         """Detaches the current parameter-gradient buffer (views of it may live on as `param.grad`) and allocates a
         new one for the next backward."""
@@ -144,6 +158,13 @@ class WeightBank:
         self._table = None
 
     # ---- descriptor table ----
+    def _upload(self, raw: bytes) -> Tensor:
+        """Host struct array -> device, from pinned memory and asynchronously (a pageable copy would stall the host
+        until the stream drains and destroy its run-ahead over the GPU)."""
+        host = torch.frombuffer(bytearray(raw), dtype=torch.uint8).pin_memory()
+        self._pinned = host   # keep alive until the copy has executed
+        return host.to(self.device, non_blocking=True)
+
     def _build_table(self) -> None:
         arr = (_lib.WeightDesc * len(self.slots))()
         for d, s in zip(arr, self.slots):
@@ -159,9 +180,7 @@ class WeightBank:
             d.stats = self.stats.data_ptr() + 8 * s.row_start
             d.rows, d.cin, d.taps, d.kpad, d.row_start = s.rows, s.cin, s.taps, s.kpad, s.row_start
             d.qkv_head_dim = s.qkv_head_dim
-        raw = bytes(arr)
-        host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
-        self._table = host.to(self.device)
+        self._table = self._upload(bytes(arr))
         self._table_ptrs = tuple(s.param.data_ptr() for s in self.slots)
 
     def _table_current(self) -> bool:
@@ -236,6 +255,7 @@ class DenoiserEngine:
         self.blocks: list[BlockPlan] = []
         self._aux_key = None
         self.grad_sync = None   # set by parallel.DistributedEDM: overlaps the gradient all-reduce with this backward
+        self._sg: Tensor | None = None   # persistent gradients of the 0-d parameters (block gains..., gain_out)
         self._build_plan()
 
     # ---- static plan ----
@@ -483,7 +503,10 @@ class DenoiserEngine:
         dev = g_D.device
         sigma = ctx["sigma"]
         nb = len(self.blocks)
-        sg = torch.zeros(nb + 1, device=dev, dtype=F32)
+        if self._sg is None or self._sg.device != dev:
+            self._sg = torch.zeros(nb + 1, device=dev, dtype=F32)
+        sg = self._sg
+        sg.zero_()
         sync = self.grad_sync
         if sync is not None:
             sync.backward_started()
@@ -538,54 +561,75 @@ class DenoiserEngine:
         dev = g_out.device
         B, Hin, Win = S["in_shape"]
         wa, wb = ops.mp_add_coeffs(bp.add_t)
+        w1, w2 = bp.w["conv_3x3_1"], bp.w["conv_3x3_2"]
         g_mid = self._attn_backward(bp, S, g_out) if bp.attn else g_out
-        # out = wb * conv2(h) + wa * xr
-        g_h = ops.conv2d(g_mid, bp.w["conv_3x3_2"].dgrad, 3, bp.cout, alpha=wb)
-        ops.conv2d_wgrad(g_mid, S["h"], bp.w["conv_3x3_2"].ghat, 3, alpha=wb)
-        g_raw = ops.modsilu_backward(g_h, S["raw"], ctx["mod"], bp.col0, d_mod, ctx["drop_p"], 0x5EED0000 + bp.index,
-                                     self.step_counter)
-        ctot = bp.cin + bp.cskip if bp.kind == "dec" else bp.cout
-        g_a = ops.conv2d(g_raw, bp.w["conv_3x3_1"].dgrad, 3, ctot)
-        ops.conv2d_wgrad(g_raw, S["a"], bp.w["conv_3x3_1"].ghat, 3)
+        # out = wb * conv2(h) + wa * xr, h = drop(mp_silu(raw * m)): the adjoint of the modulation/silu/dropout epilogue
+        # (incl. the d_mod reduction) runs in the epilogue of conv2's data gradient
+        g_raw = ops.conv2d(g_mid, w2.dgrad, 3, bp.cout, epi=EPI_MODSILU_BWD, alpha=wb, aux=S["raw"], mod=ctx["mod"],
+                           mod_off=bp.col0, d_mod=d_mod, drop_p=ctx["drop_p"], seed=0x5EED0000 + bp.index,
+                           seed_ptr=self.step_counter)
+        ops.conv2d_wgrad(g_mid, S["h"], w2.ghat, 3, alpha=wb)
+        ops.conv2d_wgrad(g_raw, S["a"], w1.ghat, 3)
         x = S["x"]
         if bp.kind == "enc":
-            if "conv_1x1" not in bp.w:
-                g_in, acc = self._take_g_in(bp, pending, (B, Hin, Win, bp.cin), dev)
-                ops.block_prep_backward(g_res=g_mid, beta=wa, g_a=g_a, x=x, nrm=S["nrm"], gain=None, d_mean=None, g_in=g_in,
-                                        g_skip=None, accumulate_in=acc, accumulate_skip=False, B=B, Hin=Hin, Win=Win,
-                                        C1=bp.cin, C2=0, resample=bp.resample, pixelnorm=True)
-                return g_in
             Hh, Ww = ops.resampled_hw(Hin, Win, bp.resample)
-            g_u = torch.empty((B, Hh, Ww, bp.cout), device=dev, dtype=BF16)
-            ops.block_prep_backward(g_res=g_mid, beta=wa, g_a=g_a, x=x, nrm=S["nrm"], gain=None, d_mean=None, g_in=g_u,
-                                    g_skip=None, accumulate_in=False, accumulate_skip=False, B=B, Hin=Hh, Win=Ww,
-                                    C1=bp.cout, C2=0, resample=RESAMPLE_NONE, pixelnorm=True)
-            g_r = ops.conv2d(g_u, bp.w["conv_1x1"].dgrad, 1, bp.cin)
-            ops.conv2d_wgrad(g_u, S["r"], bp.w["conv_1x1"].ghat, 1)
+            has_1x1 = "conv_1x1" in bp.w
+            fuse_pn = bp.cout <= 256          # the fused pixel-norm adjoint needs all channels in one N tile
+            if fuse_pn and not has_1x1 and bp.resample == RESAMPLE_NONE:
+                # conv1's data gradient, mp_silu', the residual share and the pixel-norm adjoint in ONE kernel
+                g_in, acc = self._take_g_in(bp, pending, (B, Hin, Win, bp.cin), dev)
+                ops.conv2d(g_raw, w1.dgrad, 3, bp.cout, epi=EPI_SILU_BWD, aux=x, res=g_mid, beta=wa, nrm=S["nrm"], out=g_in,
+                           accumulate_out=acc)
+                return g_in
+            if fuse_pn:
+                g_u = ops.conv2d(g_raw, w1.dgrad, 3, bp.cout, epi=EPI_SILU_BWD, aux=x, res=g_mid, beta=wa, nrm=S["nrm"])
+            else:
+                g_a = ops.conv2d(g_raw, w1.dgrad, 3, bp.cout)
+                g_u = torch.empty((B, Hh, Ww, bp.cout), device=dev, dtype=BF16)
+                ops.block_prep_backward(g_res=g_mid, beta=wa, g_a=g_a, x=x, nrm=S["nrm"], gain=None, d_mean=None, g_in=g_u,
+                                        g_skip=None, accumulate_in=False, accumulate_skip=False, B=B, Hin=Hh, Win=Ww,
+                                        C1=bp.cout, C2=0, resample=RESAMPLE_NONE, pixelnorm=True)
+            if has_1x1:
+                g_r = ops.conv2d(g_u, bp.w["conv_1x1"].dgrad, 1, bp.cin)
+                ops.conv2d_wgrad(g_u, S["r"], bp.w["conv_1x1"].ghat, 1)
+            else:
+                g_r = g_u
             g_in, acc = self._take_g_in(bp, pending, (B, Hin, Win, bp.cin), dev)
+            if bp.resample == RESAMPLE_NONE and not acc:
+                return g_r
             ops.block_prep_backward(g_res=g_r, beta=1.0, g_a=None, x=None, nrm=None, gain=None, d_mean=None, g_in=g_in,
                                     g_skip=None, accumulate_in=acc, accumulate_skip=False, B=B, Hin=Hin, Win=Win,
                                     C1=bp.cin, C2=0, resample=bp.resample, pixelnorm=False)
             return g_in
-        # ---- decoder ----
+        # ---- decoder: x = resample(cat(in, skip * gain)), a = mp_silu(x), xr = conv_1x1(x) | x ----
+        ctot = bp.cin + bp.cskip
         if "conv_1x1" in bp.w:
             g_res = ops.conv2d(g_mid, bp.w["conv_1x1"].dgrad, 1, ctot, alpha=wa)
             ops.conv2d_wgrad(g_mid, x, bp.w["conv_1x1"].ghat, 1, alpha=wa)
             beta = 1.0
         else:
             g_res, beta = g_mid, wa
+        if bp.cskip == 0 and bp.resample == RESAMPLE_NONE:
+            g_in, acc = self._take_g_in(bp, pending, (B, Hin, Win, bp.cin), dev)
+            ops.conv2d(g_raw, w1.dgrad, 3, ctot, epi=EPI_SILU_BWD, aux=x, res=g_res, beta=beta, out=g_in, accumulate_out=acc)
+            return g_in
+        # gradient w.r.t. x on the post-resample grid: conv1's data gradient * mp_silu'(x) + the residual share
+        g_x = ops.conv2d(g_raw, w1.dgrad, 3, ctot, epi=EPI_SILU_BWD, aux=x, res=g_res, beta=beta)
         if bp.cskip == 0:
             g_in, acc = self._take_g_in(bp, pending, (B, Hin, Win, bp.cin), dev)
-            ops.block_prep_backward(g_res=g_res, beta=beta, g_a=g_a, x=x, nrm=None, gain=None, d_mean=None, g_in=g_in,
+            ops.block_prep_backward(g_res=g_x, beta=1.0, g_a=None, x=None, nrm=None, gain=None, d_mean=None, g_in=g_in,
                                     g_skip=None, accumulate_in=acc, accumulate_skip=False, B=B, Hin=Hin, Win=Win,
                                     C1=bp.cin, C2=0, resample=bp.resample, pixelnorm=False)
             return g_in
         # gradient of the concatenated tensor on the pre-resample grid, then the ScaleLong adjoint, then the split
         Cs = bp.cskip
-        g_cat = torch.empty((B, Hin, Win, ctot), device=dev, dtype=BF16)
-        ops.block_prep_backward(g_res=g_res, beta=beta, g_a=g_a, x=x, nrm=None, gain=None, d_mean=None, g_in=g_cat,
-                                g_skip=None, accumulate_in=False, accumulate_skip=False, B=B, Hin=Hin, Win=Win, C1=ctot,
-                                C2=0, resample=bp.resample, pixelnorm=False)
+        if bp.resample != RESAMPLE_NONE:
+            g_cat = torch.empty((B, Hin, Win, ctot), device=dev, dtype=BF16)
+            ops.block_prep_backward(g_res=g_x, beta=1.0, g_a=None, x=None, nrm=None, gain=None, d_mean=None, g_in=g_cat,
+                                    g_skip=None, accumulate_in=False, accumulate_skip=False, B=B, Hin=Hin, Win=Win, C1=ctot,
+                                    C2=0, resample=bp.resample, pixelnorm=False)
+        else:
+            g_cat = g_x
         d_gain = torch.zeros((B, Cs), device=dev, dtype=F32)
         ops.channel_dot(g_cat, S["skip"], d_gain, Cs, bp.cin, 1.0)
         s1, s2 = bp.w["sl1"], bp.w["sl2"]
@@ -602,9 +646,15 @@ class DenoiserEngine:
         return g_in
 
     # ---- parameter / gradient enumeration in `module.parameters()` order ----
+    def begin_backward(self) -> None:
+        """See WeightBank.begin_backward; also protects the scalar-gradient buffer."""
+        self.bank.begin_backward()
+        if self._sg is not None and (self.m.gain_out.grad is not None or any(bp.gain.grad is not None for bp in self.blocks)):
+            self._sg = None
+
     def grads_by_param(self, sg: Tensor) -> dict[int, Tensor]:
-        """id(param) -> gradient tensor (views into the bank's flat buffer / the scalar gradient vector)."""
-        out = {id(s.param): s.grad for s in self.bank.slots}
+        """id(param) -> a NEW view object into the bank's flat gradient buffer / the scalar gradient vector."""
+        out = {id(s.param): g for s, g in zip(self.bank.slots, self.bank.autograd_grads())}
         for j, bp in enumerate(self.blocks):
             out[id(bp.gain)] = sg[j].view(())
         out[id(self.m.gain_out)] = sg[len(self.blocks)].view(())

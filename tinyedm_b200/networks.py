@@ -82,7 +82,7 @@ class Conv2d(nn.Module):
     def _run_backward(self, saved, gy: Tensor, need_gx: bool):
         xh, in_dtype = saved
         bank = self._bank
-        bank.ensure_grad_buffers()
+        bank.begin_backward()
         slot = bank.slots[0]
         gh = gy.permute(0, 2, 3, 1).to(BF16).contiguous()
         ops.conv2d_wgrad(gh, xh, slot.ghat, self.kernel_size)
@@ -90,7 +90,7 @@ class Conv2d(nn.Module):
         gx = None
         if need_gx:
             gx = ops.conv2d(gh, slot.dgrad, self.kernel_size, self.in_channels).permute(0, 3, 1, 2).to(in_dtype)
-        return gx, slot.grad.clone()
+        return gx, bank.autograd_grads()[0]
 
     def forward(self, x):
         return _ConvFn.apply(x, self.weight, self)
@@ -114,7 +114,7 @@ class _LinearFn(torch.autograd.Function):
     def backward(ctx, gy):
         mod, x2 = ctx.mod, ctx.x2
         bank = mod._bank
-        bank.ensure_grad_buffers()
+        bank.begin_backward()
         slot = bank.slots[0]
         g2 = gy.reshape(-1, mod.out_features).float().contiguous()
         M = x2.shape[0]
@@ -127,7 +127,7 @@ class _LinearFn(torch.autograd.Function):
             ops.sgemm(g2, slot.f32, gx, M, mod.in_features, mod.out_features, mod.out_features, mod.in_features,
                       mod.in_features, False, False)
             gx = gx.reshape(ctx.shape)
-        return gx, slot.grad.clone(), None
+        return gx, bank.autograd_grads()[0], None
 
 
 class Linear(nn.Module):
@@ -183,18 +183,21 @@ class _UncertaintyFn(torch.autograd.Function):
         mod = ctx.mod
         aug, h_pre, h, u_raw, gain = ctx.saved
         bank = mod._bank
-        bank.ensure_grad_buffers()
+        bank.begin_backward()
+        if mod._g_gain is None or mod.gain.grad is not None or mod._g_gain.device != g_u.device:
+            mod._g_gain = torch.empty((1,), device=g_u.device, dtype=F32)
         s1, s2 = bank.slots
         B, F_ = h_pre.shape
         g_u = g_u.reshape(-1).float().contiguous()
         g_uraw, g_hpre = ops.uncertainty_backward(g_u, gain, s2.f32, h_pre)
         ops.sgemm(g_uraw, h, s2.ghat, 1, F_, B, 1, F_, F_, True, False)
         ops.sgemm(g_hpre, aug, s1.ghat, F_, F_ + 1, B, F_, F_ + 1, F_ + 1, True, False)
-        g_gain = torch.empty((1,), device=g_u.device, dtype=F32)
+        g_gain = mod._g_gain
         ops.sgemm(g_u, u_raw, g_gain, 1, 1, B, 1, 1, 1, True, False)
         bank.backward()
+        g1, g2 = bank.autograd_grads()
         # fourier features carry no learnable dependency upstream (freqs/phases are buffers, sigma is data)
-        return None, s1.grad.clone(), s2.grad.clone(), g_gain.view(()), None
+        return None, g1, g2, g_gain.view(()), None
 
 
 class UncertaintyNet(nn.Module):
@@ -208,6 +211,7 @@ class UncertaintyNet(nn.Module):
         self.linear2 = Linear(hidden_features, 1)
         self.gain = nn.Parameter(torch.zeros(()))
         self._bank: WeightBank | None = None
+        self._g_gain: Tensor | None = None
 
     def _bank_for(self, dev):
         ops.ensure_device(dev)
@@ -278,7 +282,7 @@ class _EmbeddingFn(torch.autograd.Function):
         mod = ctx.mod
         fourier, pre, lab, n_sigma = ctx.saved
         bank = mod._bank
-        bank.ensure_grad_buffers()
+        bank.begin_backward()
         s_sig = bank.slots[0]
         s_cls = bank.slots[1] if len(bank.slots) > 1 else None
         B, E = pre.shape
@@ -293,7 +297,8 @@ class _EmbeddingFn(torch.autograd.Function):
         F_ = fourier.shape[1]
         ops.sgemm(g_sig, fourier, s_sig.ghat, E, F_, B, E, F_, F_, True, False)
         bank.backward()
-        return None, None, s_sig.grad.clone(), (s_cls.grad.clone() if s_cls is not None else None), None
+        grads = bank.autograd_grads()
+        return None, None, grads[0], (grads[1] if s_cls is not None else None), None
 
 
 class Embedding(nn.Module):
@@ -462,10 +467,7 @@ class _DenoiserFn(torch.autograd.Function):
         eng = ctx.mod.engine
         if ctx.saved is None:
             raise RuntimeError("tinyedm_b200.Denoiser: backward through the same forward twice is not supported")
-        # .grad tensors handed out by an earlier backward alias the engine's flat gradient buffer: if any is still
-        # alive (gradient accumulation), move the engine to a fresh buffer instead of overwriting them
-        if any(p.grad is not None for p in ctx.params):
-            eng.bank.fresh_grad_buffer()
+        eng.begin_backward()     # gradient buffers handed out earlier and still alive are not overwritten
         g_emb, sg = eng.backward(ctx.saved, g_D.float().contiguous(), need_g_emb=ctx.needs_input_grad[2])
         by_param = eng.grads_by_param(sg)
         grads = tuple(by_param[id(p)] if p.requires_grad else None for p in ctx.params)

@@ -16,7 +16,7 @@ from . import _lib
 BF16 = torch.bfloat16
 F32 = torch.float32
 
-EPI_PLAIN, EPI_MODSILU, EPI_AXPBY = 0, 1, 2
+EPI_PLAIN, EPI_MODSILU, EPI_AXPBY, EPI_MODSILU_BWD, EPI_SILU_BWD = 0, 1, 2, 3, 4
 RESAMPLE_NONE, RESAMPLE_DOWN, RESAMPLE_UP = 0, 1, 2
 
 
@@ -67,7 +67,8 @@ def weight_prep_backward(table: Tensor, n: int, total_rows: int) -> None:
 def conv2d(x: Tensor, w: Tensor, ksize: int, cout: int, *, epi: int = EPI_PLAIN, alpha: float = 1.0, beta: float = 0.0,
            res: Tensor | None = None, raw: Tensor | None = None, mod: Tensor | None = None, mod_off: int = 0,
            mod_stride: int | None = None, drop_p: float = 0.0, seed: int = 0, seed_ptr: Tensor | None = None,
-           out: Tensor | None = None, block_n: int = 0) -> Tensor:
+           out: Tensor | None = None, block_n: int = 0, aux: Tensor | None = None, d_mod: Tensor | None = None,
+           nrm: Tensor | None = None, accumulate_out: bool = False) -> Tensor:
     """Implicit-GEMM MPConv (forward or data gradient). `w` is the prepared bf16 weight [cout][k*k][cin]."""
     B, H, W, cin = x.shape
     if out is None:
@@ -77,8 +78,10 @@ def conv2d(x: Tensor, w: Tensor, ksize: int, cout: int, *, epi: int = EPI_PLAIN,
         mod_ptr = mod.data_ptr() + 4 * mod_off
         if mod_stride is None:
             mod_stride = mod.shape[1]
+    d_mod_ptr = None if d_mod is None else d_mod.data_ptr() + 4 * mod_off
     _lib.call("tedm_conv2d_forward", x.data_ptr(), w.data_ptr(), out.data_ptr(), B, H, W, cin, cout, ksize, epi, alpha,
-              _p(raw), _p(res), beta, mod_ptr, mod_stride or 0, drop_p, seed, _p(seed_ptr), block_n, _stream())
+              _p(raw), _p(res), beta, mod_ptr, mod_stride or 0, drop_p, seed, _p(seed_ptr), block_n, _p(aux), d_mod_ptr,
+              _p(nrm), 1 if accumulate_out else 0, _stream())
     return out
 
 

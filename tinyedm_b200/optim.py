@@ -87,8 +87,11 @@ class FusedAdamEMA(torch.optim.Optimizer):
             d.ema = ema.data_ptr() + 4 * o if ema is not None else None
             chunks += [(i, c) for c in range((p.numel() + chunk - 1) // chunk)]
         dev = params[0].device
-        self._table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
-        self._chunks = torch.tensor(chunks, dtype=torch.int32).to(dev)
+        # pinned + non_blocking: a pageable upload would block the host until the stream drains
+        self._host_table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory()
+        self._host_chunks = torch.tensor(chunks, dtype=torch.int32).pin_memory()
+        self._table = self._host_table.to(dev, non_blocking=True)
+        self._chunks = self._host_chunks.to(dev, non_blocking=True)
         self._n_chunks = len(chunks)
         self._table_key = key
 
