@@ -149,6 +149,21 @@ MNIST = dict(  # experiments/conf/mnist.yaml:20-56
     P_mean=-1.2, P_std=1.2, image=(1, 28, 28), batch=128)
 
 
+IMAGENET = dict(  # experiments/conf/imagenet.yaml:20-51 + the Denoiser defaults (networks.py:332-432)
+    denoiser=DenoiserSpec(
+        in_channels=4, out_channels=4, sigma_data=0.5, embedding_dim=768,
+        encoder_block_types=("Enc", "Enc", "Enc", "EncD", "Enc", "Enc", "Enc", "EncD", "EncA", "EncA", "EncA", "EncD", "EncA", "EncA", "EncA"),
+        decoder_block_types=("DecA", "Dec", "DecA", "DecA", "DecA", "DecA", "DecU", "DecA", "DecA", "DecA", "DecA", "DecU",
+                             "Dec", "Dec", "Dec", "Dec", "DecU", "Dec", "Dec", "Dec", "Dec"),
+        encoder_out_channels=(192,) * 4 + (384,) * 4 + (576,) * 4 + (768,) * 3,
+        decoder_out_channels=(768,) * 6 + (576,) * 5 + (384,) * 6 + (192,) * 4,
+        skip_connections=(False, False, True, True, True, True, False, True, True, True, True, False, True, True, True, True,
+                          False, True, True, True, True),
+        dropout_rate=0.0),
+    embedding=EmbeddingSpec(fourier_dim=192, embedding_dim=768, num_classes=1000),
+    P_mean=-0.4, P_std=1.0, image=(4, 64, 64), batch=176)
+
+
 def block_plan(spec: DenoiserSpec):
     """Static description of every block (in/out/skip channels, flags) — networks.py:447-487."""
     enc, dec = [], []

@@ -471,3 +471,37 @@ def test_mnist_config_forward_backward_vs_oracle(dev):
             worst = (k, r)
     print(f"MNIST config: D rel {rel(D, D_o):.2e}, worst tensor-gradient error {worst[1]:.2e} ({worst[0]})")
     assert worst[1] < 6e-2, worst
+
+
+def test_imagenet_latent_config_forward_backward_vs_oracle(dev):
+    """BASELINE configs[3]/[4]: the ImageNet-512 latent architecture (Denoiser defaults, 272 M parameters; 64/32/16/8 maps,
+    C = 192..768, head_dim 144 at S=256 and 192 at S=64, concat widths up to 1536), batch 1, forward and backward."""
+    import tinyedm_b200 as T
+    cfg = dict(O.IMAGENET)
+    dp, ep, _ = seeded_params(cfg, seed=11)
+    den, emb_m, _ = build_modules(cfg, dp, ep, None, dev)
+    den.eval(); emb_m.eval()
+    g = torch.Generator().manual_seed(4)
+    clean = (0.5 * torch.randn(1, 4, 64, 64, generator=g)).clamp(-1, 1)
+    sigma = torch.tensor([0.8])
+    noisy = clean + torch.randn(1, 4, 64, 64, generator=g) * 0.8
+    labels = torch.tensor([417])
+    dpo = {k: v.clone().requires_grad_(True) for k, v in dp.items()}
+    _, emb = O.embedding_forward(ep, cfg["embedding"], sigma, labels)
+    D_o = O.denoiser_forward(dpo, cfg["denoiser"], noisy, sigma, emb)
+    loss_o = O.training_loss(O.loss_weight(sigma, 0.5), D_o, clean)
+    loss_o.backward()
+    _, e = emb_m(sigma.to(dev), labels.to(dev))
+    D = den(noisy.to(dev), sigma.to(dev), e)
+    loss = T.fused_edm_loss(D, clean.to(dev), sigma.to(dev), 0.5)
+    loss.backward()
+    assert rel(D, D_o) < DRIFT_TOL and rel(loss, loss_o) < DRIFT_TOL
+    worst = ("", 0.0)
+    for k, p in den.named_parameters():
+        if p.ndim == 0:
+            continue
+        r = rel(p.grad, dpo[k].grad)
+        if r > worst[1]:
+            worst = (k, r)
+    print(f"ImageNet-latent config: D rel {rel(D, D_o):.2e}, worst tensor-gradient error {worst[1]:.2e} ({worst[0]})")
+    assert worst[1] < 6e-2, worst

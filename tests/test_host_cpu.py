@@ -77,7 +77,7 @@ def test_unet_builder_lengths():
     assert dec_t[:7] == ("DecA", "Dec", "DecA", "DecA", "DecA", "DecA", "DecU") and dec_t[-5:] == ("DecU", "Dec", "Dec", "Dec", "Dec")
 
 
-@pytest.mark.parametrize("cfg", [SMALL, cifar_cfg(num_classes=10), dict(O.MNIST)])
+@pytest.mark.parametrize("cfg", [SMALL, cifar_cfg(num_classes=10), dict(O.MNIST), dict(O.IMAGENET)])
 def test_state_dict_names_shapes_and_order_match_the_reference(cfg):
     den = T.Denoiser(**spec_kwargs(cfg["denoiser"]))
     ref = O.init_denoiser_params(cfg["denoiser"], torch.Generator().manual_seed(0))
@@ -98,6 +98,19 @@ def test_state_dict_names_shapes_and_order_match_the_reference(cfg):
     # constructor arguments mirrored as attributes (utils.deinstantiate, utils.py:15-25)
     for k, v in spec_kwargs(cfg["denoiser"]).items():
         assert getattr(den, k) == (tuple(v) if isinstance(v, (tuple, list)) else v), k
+
+
+def test_imagenet_defaults_are_the_reference_defaults():
+    """Denoiser() without arguments is the ImageNet-latent architecture (networks.py:332-432, 272.0 M parameters)."""
+    from tinyedm_b200.configs import IMAGENET, build_edm
+    m = build_edm(IMAGENET)
+    s = O.IMAGENET["denoiser"]
+    assert m.denoiser.encoder_block_types == s.encoder_block_types and m.denoiser.decoder_block_types == s.decoder_block_types
+    assert m.denoiser.encoder_out_channels == s.encoder_out_channels and m.denoiser.decoder_out_channels == s.decoder_out_channels
+    assert m.denoiser.skip_connections == s.skip_connections
+    n_den = sum(p.numel() for p in m.denoiser.parameters())
+    n_emb = sum(p.numel() for p in m.embedding.parameters())
+    assert abs(n_den - 271.997e6) < 2e3 and abs(n_emb - 0.915e6) < 1e3, (n_den, n_emb)      # BASELINE.md §2
 
 
 def test_cifar_parameter_count():

@@ -30,6 +30,15 @@ MNIST = dict(
     image=(1, 28, 28), batch=128)
 
 
+IMAGENET = dict(  # experiments/conf/imagenet.yaml:20-51; the architecture lists are the Denoiser defaults (networks.py:332-432)
+    denoiser=dict(in_channels=4, out_channels=4, sigma_data=0.5, embedding_dim=768, num_heads=4, dropout_rate=0.0),
+    embedding=dict(fourier_dim=192, embedding_dim=768, num_classes=1000),
+    diffuser=dict(P_mean=-0.4, P_std=1.0),
+    edm=dict(use_ema=True, ema_length=0.13, use_uncertainty=False, lr=0.01, steady_steps=70000, rampup_steps=2000,
+             scheduler_interval="step"),
+    image=(4, 64, 64), batch=176)
+
+
 def build_edm(cfg: dict, *, num_classes="cfg", dropout_rate=None, use_uncertainty=None):
     """EDM module for one of the dicts above (keyword overrides for the benchmark / tests)."""
     from . import EDM, Denoiser, Diffuser, Embedding

@@ -42,6 +42,9 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
 }
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(smem_u32(p)));
+}
 // c (16x8 fp32) += a (16x16 bf16, row) * b (16x8 bf16, col)
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -66,28 +69,62 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat1
   }
 }
 
+// Wide heads (> 64) do not keep their A fragments in registers: they are re-read from shared memory per k-step.
+template <int HD>
+struct KeepFrags {
+  static constexpr bool value = HD <= 64;
+};
+
 // A-operand fragments (16 rows x HD) of this warp's rows from a [rows][LD] smem tile.
 template <int HD>
 __device__ __forceinline__ void load_a_frags(uint32_t (&f)[HD / 16][4], const __nv_bfloat16* tile, int row0, int lane) {
   constexpr int LD = HD + 8;
+  if constexpr (KeepFrags<HD>::value) {
 #pragma unroll
-  for (int kk = 0; kk < HD / 16; ++kk)
-    ldsm_x4(f[kk], tile + (row0 + (lane & 15)) * LD + kk * 16 + 8 * (lane >> 4));
+    for (int kk = 0; kk < HD / 16; ++kk)
+      ldsm_x4(f[kk], tile + (row0 + (lane & 15)) * LD + kk * 16 + 8 * (lane >> 4));
+  }
 }
 
 // c[nt] (16 x 8 each, NT n-tiles starting at smem row n0) += A(16 x HD) * Bt^T where Bt is stored [n][HD] (row = n index).
+// A = this warp's 16 rows starting at a_row0 of a_tile: register fragments `a` when kept, else loaded per k-step.
 template <int HD, int NT>
-__device__ __forceinline__ void gemm_a_bt(float (&c)[NT][4], const uint32_t (&a)[HD / 16][4], const __nv_bfloat16* bt,
-                                          int n0, int lane) {
+__device__ __forceinline__ void gemm_a_bt(float (&c)[NT][4], const uint32_t (&a)[HD / 16][4], const __nv_bfloat16* a_tile,
+                                          int a_row0, const __nv_bfloat16* bt, int n0, int lane) {
   constexpr int LD = HD + 8;
+  constexpr bool KEEP = KeepFrags<HD>::value;
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
+  for (int k2 = 0; k2 < HD / 32; ++k2) {
+    uint32_t a0[4], a1[4];
+    if constexpr (KEEP) {
 #pragma unroll
-    for (int k2 = 0; k2 < HD / 32; ++k2) {
+      for (int i = 0; i < 4; ++i) { a0[i] = a[2 * k2][i]; a1[i] = a[2 * k2 + 1][i]; }
+    } else {
+      ldsm_x4(a0, a_tile + (a_row0 + (lane & 15)) * LD + (2 * k2) * 16 + 8 * (lane >> 4));
+      ldsm_x4(a1, a_tile + (a_row0 + (lane & 15)) * LD + (2 * k2 + 1) * 16 + 8 * (lane >> 4));
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
       uint32_t b[4];
       ldsm_x4(b, bt + (n0 + nt * 8 + (lane & 7)) * LD + k2 * 32 + 8 * (lane >> 3));
-      mma16816(c[nt], a[2 * k2], b[0], b[1]);
-      mma16816(c[nt], a[2 * k2 + 1], b[2], b[3]);
+      mma16816(c[nt], a0, b[0], b[1]);
+      mma16816(c[nt], a1, b[2], b[3]);
+    }
+  }
+  if constexpr (HD % 32 != 0) {   // one trailing 16-wide k-step (head_dim 144)
+    constexpr int ks = HD / 16 - 1;
+    uint32_t a0[4];
+    if constexpr (KEEP) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a0[i] = a[ks][i];
+    } else {
+      ldsm_x4(a0, a_tile + (a_row0 + (lane & 15)) * LD + ks * 16 + 8 * (lane >> 4));
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      uint32_t b[2];
+      ldsm_x2(b, bt + (n0 + nt * 8 + (lane & 7)) * LD + ks * 16 + 8 * ((lane >> 3) & 1));
+      mma16816(c[nt], a0, b[0], b[1]);
     }
   }
 }
@@ -252,7 +289,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     float s[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-    gemm_a_bt<HD, 8>(s, qf, Ks, kc, lane);
+    gemm_a_bt<HD, 8>(s, qf, Qs, warp * 16, Ks, kc, lane);
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -371,8 +408,8 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
       s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
       dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
     }
-    gemm_a_bt<HD, 8>(s, qf, Ks, kc, lane);    // S  = Q K^T
-    gemm_a_bt<HD, 8>(dp, gf, Vs, kc, lane);   // dP = dO V^T
+    gemm_a_bt<HD, 8>(s, qf, Qs, warp * 16, Ks, kc, lane);     // S  = Q K^T
+    gemm_a_bt<HD, 8>(dp, gf, dOs, warp * 16, Vs, kc, lane);   // dP = dO V^T
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
@@ -450,8 +487,8 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
       st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
       dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
     }
-    gemm_a_bt<HD, NT>(st, kf, Qs, qc, lane);     // S^T  = K Q^T   [key][query]
-    gemm_a_bt<HD, NT>(dpt, vf, dOs, qc, lane);   // dP^T = V dO^T
+    gemm_a_bt<HD, NT>(st, kf, Kb, warp * 16, Qs, qc, lane);     // S^T  = K Q^T   [key][query]
+    gemm_a_bt<HD, NT>(dpt, vf, Vb, warp * 16, dOs, qc, lane);   // dP^T = V dO^T
     uint32_t pt[NT / 2][4], dst[NT / 2][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
@@ -488,7 +525,8 @@ size_t smem_dkv(int S, int hd) {
 }
 
 int check_dims(int S, int hd, int heads) {
-  TEDM_CHECK(hd == 32 || hd == 64 || hd == 128, "attention: head_dim must be 32, 64 or 128 (got %d)", hd);
+  TEDM_CHECK(hd == 32 || hd == 64 || hd == 128 || hd == 144 || hd == 192,
+             "attention: head_dim must be one of 32, 64, 128, 144, 192 (got %d)", hd);
   TEDM_CHECK(S >= 1 && heads >= 1, "attention: empty problem");
   TEDM_CHECK(smem_dkv(S, hd) <= 227 * 1024, "attention: S=%d, head_dim=%d does not fit the shared-memory resident kernel", S, hd);
   return 0;
@@ -538,7 +576,9 @@ int attention_forward(const __nv_bfloat16* qkv, __nv_bfloat16* y, float* lse, in
   switch (hd) {
     case 32: return launch_fwd<32>(qkv, y, lse, B, S, heads, stream);
     case 64: return launch_fwd<64>(qkv, y, lse, B, S, heads, stream);
-    default: return launch_fwd<128>(qkv, y, lse, B, S, heads, stream);
+    case 128: return launch_fwd<128>(qkv, y, lse, B, S, heads, stream);
+    case 144: return launch_fwd<144>(qkv, y, lse, B, S, heads, stream);
+    default: return launch_fwd<192>(qkv, y, lse, B, S, heads, stream);
   }
 }
 
@@ -548,7 +588,9 @@ int attention_backward(const __nv_bfloat16* qkv, const __nv_bfloat16* y, const _
   switch (hd) {
     case 32: return launch_bwd<32, 64>(qkv, y, g_y, lse, delta, g_qkv, B, S, heads, stream);
     case 64: return launch_bwd<64, 64>(qkv, y, g_y, lse, delta, g_qkv, B, S, heads, stream);
-    default: return launch_bwd<128, 32>(qkv, y, g_y, lse, delta, g_qkv, B, S, heads, stream);
+    case 128: return launch_bwd<128, 32>(qkv, y, g_y, lse, delta, g_qkv, B, S, heads, stream);
+    case 144: return launch_bwd<144, 32>(qkv, y, g_y, lse, delta, g_qkv, B, S, heads, stream);
+    default: return launch_bwd<192, 32>(qkv, y, g_y, lse, delta, g_qkv, B, S, heads, stream);
   }
 }
 

@@ -482,7 +482,22 @@ int conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t stream) {
   TEDM_CHECK(conv_tile_geometry(a.H, a.W, &p.RH, &p.NB) == 0, "conv_gemm: unsupported spatial size %dx%d", a.H, a.W);
   p.tiles_h = (a.H + p.RH - 1) / p.RH;
   p.m_tiles = (p.NB == 1) ? a.B * p.tiles_h : (a.B + p.NB - 1) / p.NB;
-  int bn = a.Cout > 128 ? 256 : (a.Cout > 64 ? 128 : 64);
+  // N-tile width: the widest tile has the best operand reuse, but a grid that leaves most SMs idle (e.g. 64 tiles at
+  // 8x8, B=128) is better served by narrower tiles. Cost model: waves x (MMA time ~ BN, + fixed per-tile overhead).
+  int bn = 64;
+  {
+    long long best = -1;
+    const int cands[3] = {256, 128, 64};
+    for (int i = 0; i < 3; ++i) {
+      const int c = cands[i];
+      if (c > 64 && a.Cout <= c / 2) continue;                 // would waste more than half of the tile
+      if (a.nrm != nullptr && a.Cout > c) continue;            // fused pixel-norm adjoint needs one N tile
+      const long long tiles = (long long)p.m_tiles * ((a.Cout + c - 1) / c);
+      const long long waves = (tiles + num_sms() - 1) / num_sms();
+      const long long cost = waves * (c + 48);
+      if (best < 0 || cost < best) { best = cost; bn = c; }
+    }
+  }
   if (a.block_n_override) bn = a.block_n_override;
   p.block_n = bn;
   p.n_tiles = (a.Cout + bn - 1) / bn;
