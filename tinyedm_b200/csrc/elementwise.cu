@@ -376,6 +376,116 @@ channel_dot_kernel(const ChannelDotArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Flat fast paths (no resample, no pixel norm): pure elementwise over 8-channel vectors, 4 independent vectors per
+// thread in flight so that enough bytes are outstanding to saturate HBM.
+//   concat_silu:  x = [in | skip * gain[b]],  a = mp_silu(x)                         (networks.py:309-316)
+//   split_grad:   g_in (+)= g_cat[:, :C1];  g_skip (+)= g_cat[:, C1:] * gain[b] + d_mean[b]/HW
+// ------------------------------------------------------------------------------------------------
+constexpr int kUnroll = 4;
+
+__global__ void __launch_bounds__(256)
+concat_silu_kernel(const PrepArgs a, long long nvec_total, int vec_per_pix, int hw) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int C = a.C1 + a.C2;
+  for (long long i0 = base; i0 < nvec_total; i0 += stride * kUnroll) {
+    Vec8 x[kUnroll];
+    long long idx[kUnroll];
+    bool on[kUnroll], sk[kUnroll];
+    int cc[kUnroll];
+    long long pix[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      idx[u] = i0 + u * stride;
+      on[u] = idx[u] < nvec_total;
+      if (on[u]) {
+        pix[u] = idx[u] / vec_per_pix;
+        const int c0 = (int)(idx[u] - pix[u] * vec_per_pix) * 8;
+        sk[u] = c0 >= a.C1;
+        cc[u] = sk[u] ? c0 - a.C1 : c0;
+        x[u] = load8(sk[u] ? a.skip + pix[u] * a.C2 + cc[u] : a.in + pix[u] * a.C1 + cc[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      if (!on[u]) continue;
+      if (sk[u] && a.gain != nullptr) {
+        const Vec8 g = load8f(a.gain + (pix[u] / hw) * a.C2 + cc[u]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[u].v[i] = bf16_round(x[u].v[i] * g.v[i]);
+      }
+      const long long o = pix[u] * C + (sk[u] ? cc[u] + a.C1 : cc[u]);
+      if (a.x_out != nullptr) store8(a.x_out + o, x[u]);
+      if (a.a_out != nullptr) {
+        Vec8 sv;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sv.v[i] = mp_silu_f(x[u].v[i]);
+        store8(a.a_out + o, sv);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+split_grad_kernel(const PrepBwdArgs a, long long nvec_total, int vec_per_pix, int hw) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int C = a.C1 + a.C2;
+  const float inv_hw = 1.0f / (float)hw;
+  for (long long i0 = base; i0 < nvec_total; i0 += stride * kUnroll) {
+    Vec8 g[kUnroll], old[kUnroll];
+    bool on[kUnroll], sk[kUnroll], has_old[kUnroll];
+    int cc[kUnroll];
+    long long pix[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long idx = i0 + u * stride;
+      on[u] = idx < nvec_total;
+      has_old[u] = false;
+      if (on[u]) {
+        pix[u] = idx / vec_per_pix;
+        const int c0 = (int)(idx - pix[u] * vec_per_pix) * 8;
+        sk[u] = c0 >= a.C1;
+        cc[u] = sk[u] ? c0 - a.C1 : c0;
+        g[u] = load8(a.g_res + pix[u] * C + c0);
+        if (!sk[u] && a.accumulate_in) { old[u] = load8(a.g_in + pix[u] * a.C1 + cc[u]); has_old[u] = true; }
+        if (sk[u] && a.g_skip != nullptr && a.accumulate_skip) { old[u] = load8(a.g_skip + pix[u] * a.C2 + cc[u]); has_old[u] = true; }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      if (!on[u]) continue;
+      Vec8 o;
+      if (!sk[u]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] = g[u].v[i] * a.beta + (has_old[u] ? old[u].v[i] : 0.f);
+        store8(a.g_in + pix[u] * a.C1 + cc[u], o);
+      } else if (a.g_skip != nullptr) {
+        const long long brow = (pix[u] / hw) * a.C2 + cc[u];
+        Vec8 gn, dm;
+        if (a.gain != nullptr) gn = load8f(a.gain + brow);
+        if (a.d_mean != nullptr) dm = load8f(a.d_mean + brow);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float v = g[u].v[i] * a.beta * (a.gain != nullptr ? gn.v[i] : 1.0f);
+          if (a.d_mean != nullptr) v += dm.v[i] * inv_hw;
+          o.v[i] = v + (has_old[u] ? old[u].v[i] : 0.f);
+        }
+        store8(a.g_skip + pix[u] * a.C2 + cc[u], o);
+      }
+    }
+  }
+}
+
+int flat_grid(long long nvec) {
+  long long blocks = (nvec + 256LL * kUnroll - 1) / (256LL * kUnroll);
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
 int grid_for_warps(long long nwarps_needed, int warps_per_block) {
   long long blocks = (nwarps_needed + warps_per_block - 1) / warps_per_block;
   long long cap = (long long)num_sms() * 32;
@@ -395,6 +505,12 @@ int block_prep_forward(const PrepArgs& a, cudaStream_t stream) {
   const int W = a.resample == 1 ? a.Win / 2 : (a.resample == 2 ? a.Win * 2 : a.Win);
   const long long npix = (long long)a.B * H * W;
   if (npix == 0) return 0;
+  if (a.resample == 0 && !a.pixelnorm) {   // flat elementwise fast path
+    const long long nvec = npix * (C / 8);
+    concat_silu_kernel<<<flat_grid(nvec), 256, 0, stream>>>(a, nvec, C / 8, H * W);
+    TEDM_LAUNCH_CHECK();
+    return 0;
+  }
   const int nv = (C / 8 + 31) / 32;
   const int grid = grid_for_warps(npix, 8);
   switch (nv) {
@@ -416,6 +532,12 @@ int block_prep_backward(const PrepBwdArgs& a, cudaStream_t stream) {
   TEDM_CHECK(!(a.g_a != nullptr && a.x == nullptr), "block_prep_bwd: g_a needs x");
   const long long npix = a.resample == 1 ? (long long)a.B * (a.Hin / 2) * (a.Win / 2) : (long long)a.B * a.Hin * a.Win;
   if (npix == 0) return 0;
+  if (a.resample == 0 && !a.pixelnorm && a.g_a == nullptr) {   // flat elementwise fast path (gradient split / copy)
+    const long long nvec = npix * (C / 8);
+    split_grad_kernel<<<flat_grid(nvec), 256, 0, stream>>>(a, nvec, C / 8, a.Hin * a.Win);
+    TEDM_LAUNCH_CHECK();
+    return 0;
+  }
   const int nv = (C / 8 + 31) / 32;
   const int grid = grid_for_warps(npix, 8);
   switch (nv) {
