@@ -13,6 +13,8 @@
 // slice): the halo / zero padding comes for free from TMA out-of-bounds zero fill (negative or
 // too-large W/H coordinates). Accumulators are double buffered in TMEM (2 x BN columns) so the
 // epilogue of tile i overlaps the main loop of tile i+1.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -468,8 +470,19 @@ int conv_tile_geometry(int H, int W, int* RH, int* NB) {
   return 0;
 }
 
+// 0 = single-CTA kernel only, 1 = CTA-pair kernel wherever it applies (default), set by TEDM_CONV_PAIR
+static int conv_pair_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("TEDM_CONV_PAIR");
+    mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return mode;
+}
+
 int conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t stream) {
   TEDM_CHECK(a.ksize == 1 || a.ksize == 3, "conv_gemm: kernel size must be 1 or 3 (got %d)", a.ksize);
+  if (a.block_n_override == 0 && conv_pair_mode() == 1 && a.B > 0 && conv_pair_supported(a)) return conv_pair_launch(a, stream);
   TEDM_CHECK(a.Cin % 64 == 0, "conv_gemm: Cin must be a multiple of 64 (got %d)", a.Cin);
   TEDM_CHECK(a.Cout % 16 == 0 && a.Cout >= 16, "conv_gemm: Cout must be a multiple of 16 (got %d)", a.Cout);
   TEDM_CHECK(a.B > 0 && a.H > 0 && a.W > 0, "conv_gemm: empty input");

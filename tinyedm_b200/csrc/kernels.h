@@ -68,6 +68,9 @@ struct ConvGemmParams {
 
 int conv_tile_geometry(int H, int W, int* RH, int* NB);
 int conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t stream);
+// conv_pair.cu: the CTA-pair (tcgen05 cta_group::2) version with the TMA-staged epilogue
+bool conv_pair_supported(const ConvGemmArgs& a);
+int conv_pair_launch(const ConvGemmArgs& a, cudaStream_t stream);
 
 struct ConvWgradArgs {
   const __nv_bfloat16* g;  // (B,H,W,Cout) gradient w.r.t. the conv output
