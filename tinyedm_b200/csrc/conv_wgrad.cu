@@ -11,6 +11,8 @@
 //
 // Work item = (co block of 128, tap, ci block of <=256, K split). Accumulator 128 x 256 fp32 in TMEM.
 // Split-K partial results are combined with fp32 vector atomics into a zeroed dW.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -198,6 +200,260 @@ int wgrad_geometry(int H, int W, int* RH, int* NB) {
   return wgrad_geometry_rows(H, W, kMaxRows, RH, NB) > 0 ? 0 : -1;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair version (tcgen05 cta_group::2): one MMA of M = 256 output channels x N <= 256 input channels per 16 pixels,
+// issued by the leader CTA of a 2-CTA cluster. Each CTA stages its own 128 rows of G but only HALF of the X tile, so the
+// shared-memory data pipe carries 8 KB of operand reads per MMA and SM instead of 12 and 32 KB of TMA fill per 64
+// pixels instead of 48 (see profiles/r1c_conv_gemm_ncu_full.md). The split-K partial sums leave through swizzled
+// shared memory and TMA reduce-add (fp32) instead of 64 scattered 16-byte atomics per thread.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kPairThreads = 384;
+constexpr int kPairStagesMax = 6;
+constexpr int kPairTileBytes = 6 * 4 * kPrefRows * 128;   // 192 KB of operand stages (4 boxes per stage and CTA)
+constexpr int kPairSmemBytes = kPairTileBytes + 1024 /*align*/ + 1024 /*barriers*/;
+
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+conv_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
+                       const __grid_constant__ CUtensorMap tmap_dw, const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* full_bar = bars;                       // leader: its producer's arrival + the bytes of both CTAs' loads
+  uint64_t* empty_bar = bars + kPairStagesMax;     // MMA commit arrives in both CTAs
+  uint64_t* acc_full = bars + 2 * kPairStagesMax;  // MMA commit arrives in both CTAs
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+  smem += 1024;
+  const int kStages = p.stages;
+  const int kStageBytes = p.stage_bytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cl = (int)cluster_id_x();
+
+  // work item decode: (co block of 256, tap, ci block of <= 256, K split)
+  const int item = cl % p.items;
+  const int split = cl / p.items;
+  const int ci_blk = item % p.ci_blks;
+  const int tap = (item / p.ci_blks) % p.taps;
+  const int co_blk = item / (p.ci_blks * p.taps);
+  const int co0 = co_blk * 256 + (int)rank * 128;   // this CTA's 128 rows of the accumulator
+  const int ci0 = ci_blk * kBN;
+  int n_this = p.Cin - ci0;
+  if (n_this > kBN) n_this = kBN;
+  const int nb_half = (n_this >> 1) / 64;           // 64-channel boxes of X staged by this CTA
+  const int dr = (p.taps == 9) ? tap / 3 - 1 : 0;
+  const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
+  const int t_begin = split * p.tiles_per_split;
+  int t_end = t_begin + p.tiles_per_split;
+  if (t_end > p.p_tiles) t_end = p.p_tiles;
+  const int box_bytes = p.rows * 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_g);
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_dw);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_ptr, kBN);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_pair = 2u * (uint32_t)(2 + nb_half) * box_bytes;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int bi = t / p.tiles_h;
+        const int b0 = bi * p.NB;
+        const int h0 = (t - bi * p.tiles_h) * p.RH;
+        mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
+        uint8_t* s = smem + stage * kStageBytes;
+        const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+        if (rank == 0) mbar_expect_tx(&full_bar[stage], tx_pair);
+        tma_load_4d_pair(s, &tmap_g, full_leader, co0, 0, h0, b0);
+        tma_load_4d_pair(s + box_bytes, &tmap_g, full_leader, co0 + 64, 0, h0, b0);
+        uint8_t* xs = s + 2 * box_bytes;
+        for (int j = 0; j < nb_half; ++j)
+          tma_load_4d_pair(xs + j * box_bytes, &tmap_x, full_leader, ci0 + (int)rank * (n_this >> 1) + j * 64, ds, h0 + dr, b0);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t idesc = make_idesc_bf16(256, n_this, 1, 1);
+      const int ksteps = p.rows / 16;
+      bool first = true;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait_bounded(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+        const uint32_t b_addr = a_addr + 2 * box_bytes;
+        const uint64_t a_desc = make_smem_desc_sw128(a_addr, box_bytes, 1024);
+        const uint64_t b_desc = make_smem_desc_sw128(b_addr, box_bytes, 1024);
+        for (int k = 0; k < ksteps; ++k) {
+          umma_bf16_pair(tmem_base, a_desc + (uint64_t)(k * 128), b_desc + (uint64_t)(k * 128), idesc, first ? 0u : 1u);
+          first = false;
+        }
+        umma_commit_pair(&empty_bar[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit_pair(acc_full);
+    }
+  } else if (warp >= 4) {
+    // epilogue: 128 rows (co) x n_this columns (ci) of fp32 -> swizzled [128][32] chunks -> TMA reduce-add / store
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int m = q * 32 + lane;
+    const bool elected = (warp == 4 + 4 * half) && lane == 0;
+    if (t_end > t_begin) {
+      mbar_wait_bounded(acc_full, 0);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+      const int nch = n_this / 32;
+      const int cb = half == 0 ? 0 : nch / 2, ce = half == 0 ? nch / 2 : nch;
+      for (int c = cb; c < ce; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c * 32, r);
+        tmem_ld_wait();
+        uint8_t* buf = smem + c * (128 * 128);   // all operand stages are dead once acc_full has fired
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          float4 v = make_float4(__uint_as_float(r[g * 4 + 0]) * p.alpha, __uint_as_float(r[g * 4 + 1]) * p.alpha,
+                                 __uint_as_float(r[g * 4 + 2]) * p.alpha, __uint_as_float(r[g * 4 + 3]) * p.alpha);
+          *reinterpret_cast<float4*>(buf + m * 128 + ((g ^ (m & 7)) << 4)) = v;
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + half, 128);
+      if (elected) {
+        for (int c = cb; c < ce; ++c) {
+          const uint8_t* buf = smem + c * (128 * 128);
+          if (p.use_atomics) tma_reduce_add_2d(&tmap_dw, buf, tap * p.Cin + ci0 + c * 32, co0);
+          else tma_store_2d(&tmap_dw, buf, tap * p.Cin + ci0 + c * 32, co0);
+        }
+        bulk_commit();
+        bulk_wait_all0();
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, kBN);
+  }
+}
+
+bool wgrad_pair_supported(const ConvWgradArgs& a) {
+  if (a.Cout % 256 != 0) return false;
+  if (a.Cin % 128 != 0) return false;                    // each CTA stages whole 64-channel boxes of its half
+  if (a.Cin > 256 && a.Cin % 256 != 0) return false;
+  return true;
+}
+
+int conv_wgrad_pair_launch(const ConvWgradArgs& a, cudaStream_t stream) {
+  WgradParams p{};
+  p.B = a.B; p.H = a.H; p.W = a.W; p.Cin = a.Cin; p.Cout = a.Cout; p.taps = a.ksize * a.ksize;
+  TEDM_CHECK(wgrad_geometry(a.H, a.W, &p.RH, &p.NB) == 0, "conv_wgrad: unsupported spatial size %dx%d", a.H, a.W);
+  p.rows = p.RH * p.NB * a.W;
+  const int n_blk = a.Cin < kBN ? a.Cin : kBN;
+  p.stage_bytes = (2 + (n_blk / 2) / 64) * p.rows * 128;
+  p.stages = kPairTileBytes / p.stage_bytes;
+  if (p.stages > kPairStagesMax) p.stages = kPairStagesMax;
+  TEDM_CHECK(p.stages >= 2, "conv_wgrad: pixel tile of %d rows does not fit two pipeline stages", p.rows);
+  TEDM_CHECK(p.stages * p.stage_bytes >= (n_blk / 32) * 128 * 128, "conv_wgrad: epilogue staging does not fit");
+  p.tiles_h = (a.H + p.RH - 1) / p.RH;
+  p.p_tiles = ((a.B + p.NB - 1) / p.NB) * p.tiles_h;
+  p.co_blks = a.Cout / 256;
+  p.ci_blks = (a.Cin + kBN - 1) / kBN;
+  p.items = p.co_blks * p.ci_blks * p.taps;
+  int splits = a.splits_override;
+  const int max_clusters = num_sms() / 2;
+  if (splits <= 0) splits = max_clusters / p.items;
+  if (splits > p.p_tiles) splits = p.p_tiles;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = (p.p_tiles + splits - 1) / splits;
+  splits = (p.p_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.splits = splits;
+  p.alpha = a.alpha;
+  p.use_atomics = (splits > 1 || a.accumulate) ? 1 : 0;
+  p.dw = a.dw;
+  if (splits > 1 && !a.accumulate)
+    TEDM_CUDA(cudaMemsetAsync(a.dw, 0, sizeof(float) * (size_t)a.Cout * p.taps * a.Cin, stream));
+
+  CUtensorMap tg, tx, tdw;
+  {
+    uint64_t dims[4] = {(uint64_t)a.Cout, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
+    uint64_t strides[3] = {(uint64_t)a.Cout * 2, (uint64_t)a.W * a.Cout * 2, (uint64_t)a.H * a.W * a.Cout * 2};
+    uint32_t box[4] = {64, (uint32_t)a.W, (uint32_t)p.RH, (uint32_t)p.NB};
+    if (encode_tmap(&tg, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.g, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) != 0)
+      return -1;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.B};
+    uint64_t strides[3] = {(uint64_t)a.Cin * 2, (uint64_t)a.W * a.Cin * 2, (uint64_t)a.H * a.W * a.Cin * 2};
+    uint32_t box[4] = {64, (uint32_t)a.W, (uint32_t)p.RH, (uint32_t)p.NB};
+    if (encode_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) != 0)
+      return -1;
+  }
+  {
+    const uint64_t K = (uint64_t)p.taps * a.Cin;
+    uint64_t dims[2] = {K, (uint64_t)a.Cout};
+    uint64_t strides[1] = {K * 4};
+    uint32_t box[2] = {32, 128};
+    if (encode_tmap(&tdw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.dw, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) != 0)
+      return -1;
+  }
+  static bool configured = false;
+  if (!configured) {
+    TEDM_CUDA(cudaFuncSetAttribute(conv_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+    configured = true;
+  }
+  conv_wgrad_pair_kernel<<<2 * p.items * splits, kPairThreads, kPairSmemBytes, stream>>>(tg, tx, tdw, p);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+
+static int wgrad_pair_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("TEDM_CONV_PAIR");
+    mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return mode;
+}
+
 }  // namespace
 
 int conv_wgrad_launch(const ConvWgradArgs& a, cudaStream_t stream) {
@@ -205,6 +461,7 @@ int conv_wgrad_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   TEDM_CHECK(a.Cin % 64 == 0 && a.Cout % 64 == 0, "conv_wgrad: Cin/Cout must be multiples of 64 (got %d/%d)",
              a.Cin, a.Cout);
   TEDM_CHECK(a.B > 0 && a.H > 0 && a.W > 0, "conv_wgrad: empty input");
+  if (a.splits_override >= 0 && wgrad_pair_mode() == 1 && wgrad_pair_supported(a)) return conv_wgrad_pair_launch(a, stream);
   WgradParams p{};
   p.B = a.B; p.H = a.H; p.W = a.W; p.Cin = a.Cin; p.Cout = a.Cout; p.taps = a.ksize * a.ksize;
   TEDM_CHECK(wgrad_geometry(a.H, a.W, &p.RH, &p.NB) == 0, "conv_wgrad: unsupported spatial size %dx%d", a.H, a.W);
