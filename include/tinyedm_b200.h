@@ -39,13 +39,16 @@ typedef struct tedm_weight_desc {
   int32_t qkv_head_dim; /* != 0: qkv conv of CosineAttention — prepared rows are permuted from the reference's
                            head*3*hd + d*3 + {q,k,v} (networks.py:194) to {q,k,v}*C + head*hd + d, so the conv emits
                            de-interleaved q | k | v planes; out_fwd / out_dgrad / g_hat use the permuted row index */
-  int32_t reserved[2];
+  int32_t group_start; /* index of this tensor's first 16-row group: sum over earlier descriptors of ceil(rows/16) */
+  int32_t reserved;
 } tedm_weight_desc;
-/* table: DEVICE array of n descriptors ordered by row_start; total_rows = sum(rows).
+/* table: DEVICE array of n descriptors ordered by row_start / group_start; total_groups = sum(ceil(rows/16)).
  * training != 0 additionally rewrites every parameter in place: w <- normalize(w)  (networks.py:32-34). */
-int tedm_weight_prep_forward(const tedm_weight_desc* table, int n, int total_rows, int training, tedm_stream_t stream);
-/* dL/dw = g/s - w (w.g)/(s^2 ||w||) for every descriptor with g_hat and grad set (autograd of :35-36). */
-int tedm_weight_prep_backward(const tedm_weight_desc* table, int n, int total_rows, tedm_stream_t stream);
+int tedm_weight_prep_forward(const tedm_weight_desc* table, int n, int total_groups, int training, tedm_stream_t stream);
+/* dL/dw = g/s - w (w.g)/(s^2 ||w||) for every descriptor with g_hat and grad set (autograd of :35-36).
+ * total_rows = sum(rows); max_row_floats = max over descriptors of taps*(cin+1) (shared-memory staging of one row). */
+int tedm_weight_prep_backward(const tedm_weight_desc* table, int n, int total_rows, int max_row_floats,
+                              tedm_stream_t stream);
 
 /* ---- MPConv: F.conv2d(x, w_hat, padding="same")  (networks.py:22-43, :37) ---- */
 /* The same entry computes the data gradient: pass g as x and the out_dgrad weight layout (Cin/Cout swapped).
@@ -112,6 +115,7 @@ int tedm_embedding_backward(const float* g_emb, const float* pre, const int64_t*
 /* m[b,col] = lin[b,col]*gain[block(col)] + 1 for all blocks (networks.py:255-258): gains = device array of pointers */
 int tedm_mod_finish_forward(const float* lin, const void* gains, const int32_t* col_block, float* m, int B, int N,
                             tedm_stream_t stream);
+/* adjoint: d_lin = dm*gain; d_gain[block] += sum dm*lin (accumulated atomically: zero d_gain first) */
 int tedm_mod_finish_backward(const float* lin, const float* dm, const void* gains, const int32_t* blk_start, float* d_lin,
                              float* d_gain, int B, int N, int n_blocks, tedm_stream_t stream);
 /* ScaleLong (networks.py:106-118) on the spatial mean: gain = sigmoid(W2 mp_silu(W1 [mean,1])) */

@@ -5,10 +5,11 @@ are in scope: the module surfaces are unchanged, the arithmetic 
 reached through the C ABI in include/tinyedm_b200.h. There is no CPU path and no fallback.
 """
 from .edm import EDM, Diffuser
+from .graphs import GraphedTrainStep
 from .metric import WeightedMeanSquaredError, fused_edm_loss
 from .networks import Conv2d, Denoiser, DenoiserWrapper, Embedding, Linear, UncertaintyNet
 from .optim import FusedAdamEMA, sigma_rel_to_gamma
 from .solvers import DeterministicSolver
 
 __all__ = ["EDM", "Diffuser", "DeterministicSolver", "WeightedMeanSquaredError", "Denoiser", "Linear", "Conv2d",
-           "Embedding", "DenoiserWrapper", "UncertaintyNet", "FusedAdamEMA", "sigma_rel_to_gamma", "fused_edm_loss"]
+           "Embedding", "DenoiserWrapper", "UncertaintyNet", "FusedAdamEMA", "sigma_rel_to_gamma", "fused_edm_loss", "GraphedTrainStep"]

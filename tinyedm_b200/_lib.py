@@ -27,7 +27,8 @@ class WeightDesc(ctypes.Structure):
         ("w", c_void_p), ("grad", c_void_p), ("g_hat", c_void_p), ("out_fwd", c_void_p), ("out_dgrad", c_void_p),
         ("out_f32", c_void_p), ("stats", c_void_p),
         ("rows", ctypes.c_int32), ("cin", ctypes.c_int32), ("taps", ctypes.c_int32), ("kpad", ctypes.c_int32),
-        ("row_start", ctypes.c_int32), ("qkv_head_dim", ctypes.c_int32), ("reserved", ctypes.c_int32 * 2),
+        ("row_start", ctypes.c_int32), ("qkv_head_dim", ctypes.c_int32), ("group_start", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
 
@@ -72,9 +73,19 @@ def exported_symbols() -> list[str]:
     return list(header_signatures().keys())
 
 
+_n_calls = 0
+
+
+def n_calls() -> int:
+    """C-ABI calls issued so far by this process (== kernel launches of this library, to first order)."""
+    return _n_calls
+
+
 def call(name: str, *args) -> None:
+    global _n_calls
     if _lib is None:
         load()
+    _n_calls += 1
     rc = _fns[name](*args)
     if rc != 0:
         msg = _fns["tedm_last_error"]()

@@ -57,11 +57,12 @@ int tedm_conv2d_wgrad(const void* g, const void* x, float* dw, int B, int H, int
 #define CBF(p) static_cast<const __nv_bfloat16*>(p)
 #define ST(s) static_cast<cudaStream_t>(s)
 
-int tedm_weight_prep_forward(const tedm_weight_desc* table, int n, int total_rows, int training, tedm_stream_t stream) {
-  return weight_prep_forward(table, n, total_rows, training, ST(stream));
+int tedm_weight_prep_forward(const tedm_weight_desc* table, int n, int total_groups, int training, tedm_stream_t stream) {
+  return weight_prep_forward(table, n, total_groups, training, ST(stream));
 }
-int tedm_weight_prep_backward(const tedm_weight_desc* table, int n, int total_rows, tedm_stream_t stream) {
-  return weight_prep_backward(table, n, total_rows, ST(stream));
+int tedm_weight_prep_backward(const tedm_weight_desc* table, int n, int total_rows, int max_row_floats,
+                              tedm_stream_t stream) {
+  return weight_prep_backward(table, n, total_rows, max_row_floats, ST(stream));
 }
 
 int tedm_block_prep_forward(const void* in, const void* skip, const float* gain, void* x_out, void* a_out, float* nrm_out,

@@ -344,13 +344,23 @@ __device__ __forceinline__ float bf16_round(float x) {
 
 constexpr float kSiluInv = 1.0f / 0.596f;
 
+// One SFU op per element: sigmoid(x) = 0.5 + 0.5 tanh(x/2) with MUFU.TANH (abs. error ~2^-11, far below the bf16
+// rounding of every consumer). The exp + reciprocal form costs two SFU ops, and at 16 SFU lanes per SM and clock that
+// alone made the activation kernels SFU-bound (134 M elements of a 32x32x256 B=256 tensor = 60 us) before HBM-bound.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
+
 // mp_silu (networks.py:83-84): silu(x) / 0.596
 __device__ __forceinline__ float mp_silu_f(float x) {
-  return x * kSiluInv / (1.0f + __expf(-x));
+  return x * kSiluInv * sigmoid_f(x);
 }
 // d/dx mp_silu(x) = sigma(x) * (1 + x * (1 - sigma(x))) / 0.596
 __device__ __forceinline__ float mp_silu_grad_f(float x) {
-  float s = 1.0f / (1.0f + __expf(-x));
+  const float s = sigmoid_f(x);
   return s * (1.0f + x * (1.0f - s)) * kSiluInv;
 }
 

@@ -29,6 +29,13 @@ __device__ __forceinline__ Vec8 load8(const __nv_bfloat16* p) {
   r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
   return r;
 }
+__device__ __forceinline__ uint4 load_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ Vec8 unpack8(const uint4 u) {
+  Vec8 r;
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
+  return r;
+}
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const Vec8& r) {
   uint4 u;
   u.x = pack_bf16(r.v[0], r.v[1]); u.y = pack_bf16(r.v[2], r.v[3]);
@@ -45,74 +52,104 @@ __device__ __forceinline__ Vec8 load8f(const float* p) {
 // ------------------------------------------------------------------------------------------------
 // block_prep forward
 // ------------------------------------------------------------------------------------------------
-template <int NV>
-__global__ void __launch_bounds__(256)
+// PU pixels per warp are in flight at once: every load of the group is issued before the first use and stays PACKED
+// (4 registers per 8 channels) until then, so that >= 4 CTAs of 256 threads fit on an SM: HBM needs ~64-128 KB of
+// loads in flight per SM, which one 16-byte load per thread at low occupancy does not provide. Index math is 32-bit.
+// kPool: the 2x2 average-pool variant (4 loads per output vector, averaged in fp32 on arrival).
+template <int NV, int PU, bool kPool>
+__global__ void __launch_bounds__(256, (NV * PU <= 4) ? 4 : 2)
 block_prep_fwd_kernel(const PrepArgs a) {
   const int H = a.resample == 1 ? a.Hin / 2 : (a.resample == 2 ? a.Hin * 2 : a.Hin);
   const int W = a.resample == 1 ? a.Win / 2 : (a.resample == 2 ? a.Win * 2 : a.Win);
   const int C = a.C1 + a.C2;
   const int nvec = C / 8;
-  const long long npix = (long long)a.B * H * W;
+  const int HW = H * W;
+  const int npix = a.B * HW;
   const int lane = threadIdx.x & 31;
-  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long pix = warp0; pix < npix; pix += nwarps) {
-    const int w = (int)(pix % W);
-    const int h = (int)((pix / W) % H);
-    const int b = (int)(pix / ((long long)W * H));
-    Vec8 val[NV];
-    float ss = 0.f;
+  const int warp0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  for (int pix0 = warp0 * PU; pix0 < npix; pix0 += nwarps * PU) {
+    uint4 raw[PU][NV];
+    Vec8 pooled[kPool ? PU : 1][kPool ? NV : 1];
+    int bb[PU];
 #pragma unroll
-    for (int it = 0; it < NV; ++it) {
-      const int v = lane + it * 32;
-      if (v < nvec) {
-        const int c0 = v * 8;
-        const bool from_skip = c0 >= a.C1;
-        const __nv_bfloat16* src = from_skip ? a.skip : a.in;
-        const int cs = from_skip ? a.C2 : a.C1;
-        const int cc = from_skip ? c0 - a.C1 : c0;
-        Vec8 x;
-        if (a.resample == 1) {
-          const long long base = (((long long)b * a.Hin + 2 * h) * a.Win + 2 * w) * cs + cc;
-          Vec8 p0 = load8(src + base), p1 = load8(src + base + cs);
-          Vec8 p2 = load8(src + base + (long long)a.Win * cs), p3 = load8(src + base + (long long)a.Win * cs + cs);
+    for (int u = 0; u < PU; ++u) {
+      const int pix = pix0 + u;
+      bb[u] = 0;
+      if (pix < npix) {
+        const int b = pix / HW;
+        const int rem = pix - b * HW;
+        const int h = rem / W;
+        const int w = rem - h * W;
+        bb[u] = b;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) x.v[i] = 0.25f * (p0.v[i] + p1.v[i] + p2.v[i] + p3.v[i]);
-        } else {
-          const int hs = a.resample == 2 ? h >> 1 : h, ws = a.resample == 2 ? w >> 1 : w;
-          x = load8(src + (((long long)b * a.Hin + hs) * a.Win + ws) * cs + cc);
+        for (int it = 0; it < NV; ++it) {
+          const int v = lane + it * 32;
+          if (v < nvec) {
+            const int c0 = v * 8;
+            const bool from_skip = c0 >= a.C1;
+            const __nv_bfloat16* src = from_skip ? a.skip : a.in;
+            const int cs = from_skip ? a.C2 : a.C1;
+            const int cc = from_skip ? c0 - a.C1 : c0;
+            if constexpr (kPool) {
+              const long long base = (((long long)b * a.Hin + 2 * h) * a.Win + 2 * w) * cs + cc;
+              const Vec8 p0 = load8(src + base), p1 = load8(src + base + cs);
+              const Vec8 p2 = load8(src + base + (long long)a.Win * cs), p3 = load8(src + base + (long long)a.Win * cs + cs);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pooled[u][it].v[i] = 0.25f * (p0.v[i] + p1.v[i] + p2.v[i] + p3.v[i]);
+            } else {
+              const int hs = a.resample == 2 ? h >> 1 : h, ws = a.resample == 2 ? w >> 1 : w;
+              raw[u][it] = load_raw(src + (((long long)b * a.Hin + hs) * a.Win + ws) * cs + cc);
+            }
+          }
         }
-        if (from_skip && a.gain != nullptr) {
-          Vec8 g = load8f(a.gain + (long long)b * a.C2 + cc);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) x.v[i] *= g.v[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) ss += x.v[i] * x.v[i];
-        val[it] = x;
       }
     }
-    float inv_n = 1.0f;
-    if (a.pixelnorm) {
-      ss = warp_sum(ss);
-      const float n = kEps + sqrtf(ss / (float)C);
-      inv_n = 1.0f / n;
-      if (a.nrm_out != nullptr && lane == 0) a.nrm_out[pix] = n;
-    }
 #pragma unroll
-    for (int it = 0; it < NV; ++it) {
-      const int v = lane + it * 32;
-      if (v < nvec) {
-        Vec8 x = val[it];
+    for (int u = 0; u < PU; ++u) {
+      const int pix = pix0 + u;
+      if (pix < npix) {   // warp-uniform
+        Vec8 val[NV];
+        float ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x.v[i] = bf16_round(x.v[i] * inv_n);
-        const long long o = pix * C + v * 8;
-        if (a.x_out != nullptr) store8(a.x_out + o, x);
-        if (a.a_out != nullptr) {
-          Vec8 s;
+        for (int it = 0; it < NV; ++it) {
+          const int v = lane + it * 32;
+          if (v < nvec) {
+            if constexpr (kPool) val[it] = pooled[u][it];
+            else val[it] = unpack8(raw[u][it]);
+            const int c0 = v * 8;
+            if (c0 >= a.C1 && a.gain != nullptr) {
+              const Vec8 g = load8f(a.gain + (long long)bb[u] * a.C2 + (c0 - a.C1));
 #pragma unroll
-          for (int i = 0; i < 8; ++i) s.v[i] = mp_silu_f(x.v[i]);
-          store8(a.a_out + o, s);
+              for (int i = 0; i < 8; ++i) val[it].v[i] *= g.v[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ss += val[it].v[i] * val[it].v[i];
+          }
+        }
+        float inv_n = 1.0f;
+        if (a.pixelnorm) {
+          ss = warp_sum(ss);
+          const float n = kEps + sqrtf(ss / (float)C);
+          inv_n = 1.0f / n;
+          if (a.nrm_out != nullptr && lane == 0) a.nrm_out[pix] = n;
+        }
+#pragma unroll
+        for (int it = 0; it < NV; ++it) {
+          const int v = lane + it * 32;
+          if (v < nvec) {
+            Vec8 x = val[it];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x.v[i] = bf16_round(x.v[i] * inv_n);
+            const long long o = (long long)pix * C + v * 8;
+            if (a.x_out != nullptr) store8(a.x_out + o, x);
+            if (a.a_out != nullptr) {
+              Vec8 sv;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) sv.v[i] = mp_silu_f(x.v[i]);
+              store8(a.a_out + o, sv);
+            }
+          }
         }
       }
     }
@@ -274,6 +311,139 @@ block_prep_bwd_kernel(const PrepBwdArgs a) {
   }
 }
 
+// Light variant (no mp_silu / pixel-norm adjoint: g_a == null, !pixelnorm), which is every standalone launch of the
+// CIFAR plan (resample adjoints, concat split, accumulation into a pending skip gradient). PU destination pixels per warp
+// in flight, 32-bit index math.
+template <int NV, int PU, bool kUp>
+__global__ void __launch_bounds__(256, (NV * PU <= 4 && !kUp) ? 3 : 2)
+block_prep_bwd_light_kernel(const PrepBwdArgs a) {
+  const int C = a.C1 + a.C2;
+  const int nvec = C / 8;
+  const int lane = threadIdx.x & 31;
+  const int warp0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int HWin = a.Hin * a.Win;
+  const float inv_hw = 1.0f / (float)HWin;
+  if (a.resample == 1) {
+    // adjoint of the 2x2 average pool: iterate over pooled pixels, write 4 children
+    const int H = a.Hin / 2, W = a.Win / 2;
+    const int npix = a.B * H * W;
+    for (int pix0 = warp0 * PU; pix0 < npix; pix0 += nwarps * PU) {
+      Vec8 g[PU][NV];
+#pragma unroll
+      for (int u = 0; u < PU; ++u)
+        if (pix0 + u < npix)
+#pragma unroll
+          for (int it = 0; it < NV; ++it)
+            if (lane + it * 32 < nvec) g[u][it] = load8(a.g_res + (long long)(pix0 + u) * C + (lane + it * 32) * 8);
+#pragma unroll
+      for (int u = 0; u < PU; ++u) {
+        const int pix = pix0 + u;
+        if (pix < npix) {
+          const int b = pix / (H * W);
+          const int rem = pix - b * H * W;
+          const int h = rem / W, w = rem - h * W;
+#pragma unroll
+          for (int it = 0; it < NV; ++it) {
+            const int v = lane + it * 32;
+            if (v < nvec) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) g[u][it].v[i] *= a.beta;
+              for (int dy = 0; dy < 2; ++dy)
+                for (int dx = 0; dx < 2; ++dx)
+                  prep_bwd_store(a, b, ((long long)b * a.Hin + 2 * h + dy) * a.Win + 2 * w + dx, v, g[u][it], 0.25f);
+            }
+          }
+        }
+      }
+    }
+    return;
+  }
+  // destination pixels live on the (Hin, Win) grid; with resample == 2 each sums its 2x2 children of g_res
+  const int npix = a.B * HWin;
+  const int W2 = a.Win * 2;
+  for (int pix0 = warp0 * PU; pix0 < npix; pix0 += nwarps * PU) {
+    uint4 g[PU][NV][kUp ? 4 : 1], old[PU][NV];
+    int bb[PU];
+#pragma unroll
+    for (int u = 0; u < PU; ++u) {
+      const int pix = pix0 + u;
+      bb[u] = 0;
+      if (pix < npix) {
+        const int b = pix / HWin;
+        bb[u] = b;
+#pragma unroll
+        for (int it = 0; it < NV; ++it) {
+          const int v = lane + it * 32;
+          if (v < nvec) {
+            const int c0 = v * 8;
+            if constexpr (kUp) {
+              const int rem = pix - b * HWin;
+              const int hs = rem / a.Win, ws = rem - hs * a.Win;
+              const long long base = (((long long)b * (2 * a.Hin) + 2 * hs) * W2 + 2 * ws) * C + c0;
+              g[u][it][0] = load_raw(a.g_res + base);
+              g[u][it][1] = load_raw(a.g_res + base + C);
+              g[u][it][2] = load_raw(a.g_res + base + (long long)W2 * C);
+              g[u][it][3] = load_raw(a.g_res + base + (long long)W2 * C + C);
+            } else {
+              g[u][it][0] = load_raw(a.g_res + (long long)pix * C + c0);
+            }
+            // previous contents of the destination (accumulation) are fetched in the same batch of loads
+            if (c0 < a.C1) {
+              if (a.accumulate_in) old[u][it] = load_raw(a.g_in + (long long)pix * a.C1 + c0);
+            } else if (a.g_skip != nullptr && a.accumulate_skip) {
+              old[u][it] = load_raw(a.g_skip + (long long)pix * a.C2 + (c0 - a.C1));
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PU; ++u) {
+      const int pix = pix0 + u;
+      if (pix < npix) {
+#pragma unroll
+        for (int it = 0; it < NV; ++it) {
+          const int v = lane + it * 32;
+          if (v < nvec) {
+            const int c0 = v * 8;
+            Vec8 gv = unpack8(g[u][it][0]);
+            if constexpr (kUp) {
+#pragma unroll
+              for (int k = 1; k < 4; ++k) {
+                const Vec8 t = unpack8(g[u][it][k]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) gv.v[i] += t.v[i];
+              }
+            }
+            Vec8 o;
+            if (c0 < a.C1) {
+              Vec8 ov;
+              if (a.accumulate_in) ov = unpack8(old[u][it]);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o.v[i] = gv.v[i] * a.beta + (a.accumulate_in ? ov.v[i] : 0.f);
+              store8(a.g_in + (long long)pix * a.C1 + c0, o);
+            } else if (a.g_skip != nullptr) {
+              const int cc = c0 - a.C1;
+              Vec8 gn, dm, ov;
+              if (a.gain != nullptr) gn = load8f(a.gain + (long long)bb[u] * a.C2 + cc);
+              if (a.d_mean != nullptr) dm = load8f(a.d_mean + (long long)bb[u] * a.C2 + cc);
+              if (a.accumulate_skip) ov = unpack8(old[u][it]);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float t = gv.v[i] * a.beta * (a.gain != nullptr ? gn.v[i] : 1.0f);
+                if (a.d_mean != nullptr) t += dm.v[i] * inv_hw;
+                o.v[i] = t + (a.accumulate_skip ? ov.v[i] : 0.f);
+              }
+              store8(a.g_skip + (long long)pix * a.C2 + cc, o);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // modsilu backward:  h = drop(mp_silu(r * m));  given g_h:
 //   g_z = g_h * keep/(1-p) * mp_silu'(r*m);  g_r = g_z * m;  dm[b,c] += sum_hw g_z * r
@@ -337,7 +507,7 @@ modsilu_bwd_kernel(const ModSiluBwdArgs a) {
 // ------------------------------------------------------------------------------------------------
 // channel_dot: out[b, c] (+)= scale * sum_p A[b,p,a_off + c] * (Bm ? Bm[b,p,c] : 1)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 channel_dot_kernel(const ChannelDotArgs a) {
   extern __shared__ float sred[];
   const int nvec = a.C / 8;
@@ -353,16 +523,31 @@ channel_dot_kernel(const ChannelDotArgs a) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   if (rr < rows) {
-    for (int p = p_begin + rr; p < p_end; p += rows) {
-      const long long pa = ((long long)b * a.HW + p) * a.CA + a.a_off + v * 8;
-      Vec8 x = load8(a.A + pa);
-      if (a.Bm != nullptr) {
-        Vec8 y = load8(a.Bm + ((long long)b * a.HW + p) * a.C + v * 8);
+    constexpr int U = 4;   // independent 16-byte loads in flight per operand
+    for (int p = p_begin + rr; p < p_end; p += rows * U) {
+      uint4 xr[U], yr[U];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += x.v[i] * y.v[i];
-      } else {
+      for (int u = 0; u < U; ++u) {
+        const int pp = p + u * rows;
+        if (pp < p_end) {
+          const long long row = (long long)b * a.HW + pp;
+          xr[u] = load_raw(a.A + row * a.CA + a.a_off + v * 8);
+          if (a.Bm != nullptr) yr[u] = load_raw(a.Bm + row * a.C + v * 8);
+        }
+      }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += x.v[i];
+      for (int u = 0; u < U; ++u) {
+        if (p + u * rows < p_end) {
+          const Vec8 x = unpack8(xr[u]);
+          if (a.Bm != nullptr) {
+            const Vec8 y = unpack8(yr[u]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += x.v[i] * y.v[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += x.v[i];
+          }
+        }
       }
     }
 #pragma unroll
@@ -377,118 +562,9 @@ channel_dot_kernel(const ChannelDotArgs a) {
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// Flat fast paths (no resample, no pixel norm): pure elementwise over 8-channel vectors, 4 independent vectors per
-// thread in flight so that enough bytes are outstanding to saturate HBM.
-//   concat_silu:  x = [in | skip * gain[b]],  a = mp_silu(x)                         (networks.py:309-316)
-//   split_grad:   g_in (+)= g_cat[:, :C1];  g_skip (+)= g_cat[:, C1:] * gain[b] + d_mean[b]/HW
-// ------------------------------------------------------------------------------------------------
-constexpr int kUnroll = 4;
-
-__global__ void __launch_bounds__(256)
-concat_silu_kernel(const PrepArgs a, long long nvec_total, int vec_per_pix, int hw) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int C = a.C1 + a.C2;
-  for (long long i0 = base; i0 < nvec_total; i0 += stride * kUnroll) {
-    Vec8 x[kUnroll];
-    long long idx[kUnroll];
-    bool on[kUnroll], sk[kUnroll];
-    int cc[kUnroll];
-    long long pix[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      idx[u] = i0 + u * stride;
-      on[u] = idx[u] < nvec_total;
-      if (on[u]) {
-        pix[u] = idx[u] / vec_per_pix;
-        const int c0 = (int)(idx[u] - pix[u] * vec_per_pix) * 8;
-        sk[u] = c0 >= a.C1;
-        cc[u] = sk[u] ? c0 - a.C1 : c0;
-        x[u] = load8(sk[u] ? a.skip + pix[u] * a.C2 + cc[u] : a.in + pix[u] * a.C1 + cc[u]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      if (!on[u]) continue;
-      if (sk[u] && a.gain != nullptr) {
-        const Vec8 g = load8f(a.gain + (pix[u] / hw) * a.C2 + cc[u]);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[u].v[i] = bf16_round(x[u].v[i] * g.v[i]);
-      }
-      const long long o = pix[u] * C + (sk[u] ? cc[u] + a.C1 : cc[u]);
-      if (a.x_out != nullptr) store8(a.x_out + o, x[u]);
-      if (a.a_out != nullptr) {
-        Vec8 sv;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sv.v[i] = mp_silu_f(x[u].v[i]);
-        store8(a.a_out + o, sv);
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256)
-split_grad_kernel(const PrepBwdArgs a, long long nvec_total, int vec_per_pix, int hw) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int C = a.C1 + a.C2;
-  const float inv_hw = 1.0f / (float)hw;
-  for (long long i0 = base; i0 < nvec_total; i0 += stride * kUnroll) {
-    Vec8 g[kUnroll], old[kUnroll];
-    bool on[kUnroll], sk[kUnroll], has_old[kUnroll];
-    int cc[kUnroll];
-    long long pix[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const long long idx = i0 + u * stride;
-      on[u] = idx < nvec_total;
-      has_old[u] = false;
-      if (on[u]) {
-        pix[u] = idx / vec_per_pix;
-        const int c0 = (int)(idx - pix[u] * vec_per_pix) * 8;
-        sk[u] = c0 >= a.C1;
-        cc[u] = sk[u] ? c0 - a.C1 : c0;
-        g[u] = load8(a.g_res + pix[u] * C + c0);
-        if (!sk[u] && a.accumulate_in) { old[u] = load8(a.g_in + pix[u] * a.C1 + cc[u]); has_old[u] = true; }
-        if (sk[u] && a.g_skip != nullptr && a.accumulate_skip) { old[u] = load8(a.g_skip + pix[u] * a.C2 + cc[u]); has_old[u] = true; }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      if (!on[u]) continue;
-      Vec8 o;
-      if (!sk[u]) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o.v[i] = g[u].v[i] * a.beta + (has_old[u] ? old[u].v[i] : 0.f);
-        store8(a.g_in + pix[u] * a.C1 + cc[u], o);
-      } else if (a.g_skip != nullptr) {
-        const long long brow = (pix[u] / hw) * a.C2 + cc[u];
-        Vec8 gn, dm;
-        if (a.gain != nullptr) gn = load8f(a.gain + brow);
-        if (a.d_mean != nullptr) dm = load8f(a.d_mean + brow);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float v = g[u].v[i] * a.beta * (a.gain != nullptr ? gn.v[i] : 1.0f);
-          if (a.d_mean != nullptr) v += dm.v[i] * inv_hw;
-          o.v[i] = v + (has_old[u] ? old[u].v[i] : 0.f);
-        }
-        store8(a.g_skip + pix[u] * a.C2 + cc[u], o);
-      }
-    }
-  }
-}
-
-int flat_grid(long long nvec) {
-  long long blocks = (nvec + 256LL * kUnroll - 1) / (256LL * kUnroll);
-  const long long cap = (long long)num_sms() * 16;
-  if (blocks > cap) blocks = cap;
-  return (int)(blocks < 1 ? 1 : blocks);
-}
-
 int grid_for_warps(long long nwarps_needed, int warps_per_block) {
   long long blocks = (nwarps_needed + warps_per_block - 1) / warps_per_block;
-  long long cap = (long long)num_sms() * 32;
+  long long cap = (long long)num_sms() * 64;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
@@ -505,20 +581,21 @@ int block_prep_forward(const PrepArgs& a, cudaStream_t stream) {
   const int W = a.resample == 1 ? a.Win / 2 : (a.resample == 2 ? a.Win * 2 : a.Win);
   const long long npix = (long long)a.B * H * W;
   if (npix == 0) return 0;
-  if (a.resample == 0 && !a.pixelnorm) {   // flat elementwise fast path
-    const long long nvec = npix * (C / 8);
-    concat_silu_kernel<<<flat_grid(nvec), 256, 0, stream>>>(a, nvec, C / 8, H * W);
-    TEDM_LAUNCH_CHECK();
-    return 0;
-  }
+  TEDM_CHECK(npix < (1LL << 31) / 8, "block_prep: too many pixels");
   const int nv = (C / 8 + 31) / 32;
-  const int grid = grid_for_warps(npix, 8);
   switch (nv) {
-    case 1: block_prep_fwd_kernel<1><<<grid, 256, 0, stream>>>(a); break;
-    case 2: block_prep_fwd_kernel<2><<<grid, 256, 0, stream>>>(a); break;
-    case 3: block_prep_fwd_kernel<3><<<grid, 256, 0, stream>>>(a); break;
-    case 4: block_prep_fwd_kernel<4><<<grid, 256, 0, stream>>>(a); break;
-    default: block_prep_fwd_kernel<6><<<grid, 256, 0, stream>>>(a); break;
+#define TEDM_PREP_FWD(NV, PU)                                                                                         \
+  do {                                                                                                                \
+    const int grid = grid_for_warps((npix + PU - 1) / PU, 8);                                                         \
+    if (a.resample == 1) block_prep_fwd_kernel<NV, 1, true><<<grid_for_warps(npix, 8), 256, 0, stream>>>(a);          \
+    else block_prep_fwd_kernel<NV, PU, false><<<grid, 256, 0, stream>>>(a);                                           \
+  } while (0)
+    case 1: TEDM_PREP_FWD(1, 4); break;
+    case 2: TEDM_PREP_FWD(2, 2); break;
+    case 3: TEDM_PREP_FWD(3, 2); break;
+    case 4: TEDM_PREP_FWD(4, 1); break;
+    default: TEDM_PREP_FWD(6, 1); break;
+#undef TEDM_PREP_FWD
   }
   TEDM_LAUNCH_CHECK();
   return 0;
@@ -532,9 +609,23 @@ int block_prep_backward(const PrepBwdArgs& a, cudaStream_t stream) {
   TEDM_CHECK(!(a.g_a != nullptr && a.x == nullptr), "block_prep_bwd: g_a needs x");
   const long long npix = a.resample == 1 ? (long long)a.B * (a.Hin / 2) * (a.Win / 2) : (long long)a.B * a.Hin * a.Win;
   if (npix == 0) return 0;
-  if (a.resample == 0 && !a.pixelnorm && a.g_a == nullptr) {   // flat elementwise fast path (gradient split / copy)
-    const long long nvec = npix * (C / 8);
-    split_grad_kernel<<<flat_grid(nvec), 256, 0, stream>>>(a, nvec, C / 8, a.Hin * a.Win);
+  TEDM_CHECK(npix < (1LL << 31) / 8, "block_prep_bwd: too many pixels");
+  if (!a.pixelnorm && a.g_a == nullptr) {   // residual gradient only: resample adjoint / concat split / accumulation
+    const long long ndst = a.resample == 1 ? npix : (long long)a.B * a.Hin * a.Win;
+    const int nvl = (C / 8 + 31) / 32;
+    switch (nvl) {
+#define TEDM_PREP_BWD(NV, PU)                                                                                         \
+  do {                                                                                                                \
+    if (a.resample == 2) block_prep_bwd_light_kernel<NV, 1, true><<<grid_for_warps(ndst, 8), 256, 0, stream>>>(a);    \
+    else block_prep_bwd_light_kernel<NV, PU, false><<<grid_for_warps((ndst + PU - 1) / PU, 8), 256, 0, stream>>>(a);  \
+  } while (0)
+      case 1: TEDM_PREP_BWD(1, 4); break;
+      case 2: TEDM_PREP_BWD(2, 2); break;
+      case 3: TEDM_PREP_BWD(3, 1); break;
+      case 4: TEDM_PREP_BWD(4, 1); break;
+      default: TEDM_PREP_BWD(6, 1); break;
+#undef TEDM_PREP_BWD
+    }
     TEDM_LAUNCH_CHECK();
     return 0;
   }

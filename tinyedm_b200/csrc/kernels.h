@@ -11,8 +11,8 @@
 namespace tedm {
 
 typedef tedm_weight_desc WeightDesc;
-int weight_prep_forward(const WeightDesc* table_dev, int n_tensors, int total_rows, int training, cudaStream_t stream);
-int weight_prep_backward(const WeightDesc* table_dev, int n_tensors, int total_rows, cudaStream_t stream);
+int weight_prep_forward(const WeightDesc* table_dev, int n_tensors, int total_groups, int training, cudaStream_t stream);
+int weight_prep_backward(const WeightDesc* table_dev, int n_tensors, int total_rows, int max_row_floats, cudaStream_t stream);
 
 enum ConvEpilogue : int {
   EPI_PLAIN = 0,    // out = alpha * acc

@@ -140,7 +140,8 @@ __global__ void mod_finish_fwd_kernel(const float* __restrict__ lin, const float
   m[i] = lin[i] * *gains[col_block[col]] + 1.0f;
 }
 
-// one CTA per block id: d_gain[blk] = sum dm*lin over its columns; d_lin = dm * gain
+// grid (block id, batch chunk): d_gain[blk] += sum dm*lin over the block's columns (atomic; zeroed by the caller);
+// d_lin = dm * gain
 __global__ void __launch_bounds__(256)
 mod_finish_bwd_kernel(const float* __restrict__ lin, const float* __restrict__ dm, const float* const* __restrict__ gains,
                       const int* __restrict__ blk_start, float* __restrict__ d_lin, float* __restrict__ d_gain, int B,
@@ -151,20 +152,22 @@ mod_finish_bwd_kernel(const float* __restrict__ lin, const float* __restrict__ d
   const int w = c1 - c0;
   const float g = *gains[blk];
   float acc = 0.f;
-  for (int i = threadIdx.x; i < B * w; i += blockDim.x) {
-    const int b = i / w, c = c0 + i - b * w;
-    const size_t o = (size_t)b * N + c;
-    const float d = dm[o];
-    acc += d * lin[o];
-    d_lin[o] = d * g;
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
+      const size_t o = (size_t)b * N + c;
+      const float d = dm[o];
+      acc += d * lin[o];
+      d_lin[o] = d * g;
+    }
   }
+  (void)w;
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += red[i];
-    d_gain[blk] = t;
+    atomicAdd(d_gain + blk, t);
   }
 }
 
@@ -364,66 +367,103 @@ conv_out_fwd_kernel(const ConvOutArgs a) {
 
 __global__ void __launch_bounds__(256)
 conv_out_bwd_kernel(const ConvOutBwdArgs a) {
+  // Each lane owns groups of 8 consecutive channels (one 16-byte access per pixel); a warp walks pixels.
+  //   g_f = g_D * c_out(sigma_b);  d gain_out += g_f * f_raw;  g_x = gain_out * sum_o g_f[o] w[o];  dW[o] += gain_out g_f[o] x
   extern __shared__ float sm[];  // [warps][Co*C] partial dW
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const long long npix = (long long)a.B * a.HW;
   const long long warp0 = (long long)blockIdx.x * nw + wib;
   const long long nwarps = (long long)gridDim.x * nw;
-  const int per_lane = a.C / 32;  // channels per lane (C % 64 == 0 -> even)
-  float dw[kMaxCo][8];            // supports C <= 256 per lane chunk of 8; loop chunks otherwise
+  const int ngroups = a.C / 8;
   float dgain = 0.f;
   const float gain_out = *a.gain_out;
-  // channel ownership: lane owns channels [lane*per_lane, (lane+1)*per_lane)
-  for (int cc = 0; cc < per_lane; cc += 8) {
-    const int nch = per_lane - cc < 8 ? per_lane - cc : 8;
+  const float sd = a.sigma_data;
+  for (int i = threadIdx.x; i < nw * a.Co * a.C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  for (int cg0 = 0; cg0 < ngroups; cg0 += 32) {
+    const int cg = cg0 + lane;
+    const bool on = cg < ngroups;
+    float wv[kMaxCo][8], dw[kMaxCo][8];
 #pragma unroll
-    for (int o = 0; o < kMaxCo; ++o)
+    for (int o = 0; o < kMaxCo; ++o) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dw[o][i] = 0.f;
-    for (long long pix = warp0; pix < npix; pix += nwarps) {
-      const int b = (int)(pix / a.HW);
-      const int p = (int)(pix - (long long)b * a.HW);
-      const float s = a.sigma[b * a.sigma_stride];
-      const float sd = a.sigma_data;
-      const float c_out = s * sd * rsqrtf(s * s + sd * sd);
-      float gf[kMaxCo];
+      for (int i = 0; i < 8; ++i) { wv[o][i] = 0.f; dw[o][i] = 0.f; }
+      if (on && o < a.Co) {
+        const uint4 u = *reinterpret_cast<const uint4*>(a.w + (size_t)o * a.C + cg * 8);
+        const float2 p0 = unpack_bf16(u.x), p1 = unpack_bf16(u.y), p2 = unpack_bf16(u.z), p3 = unpack_bf16(u.w);
+        wv[o][0] = p0.x; wv[o][1] = p0.y; wv[o][2] = p1.x; wv[o][3] = p1.y;
+        wv[o][4] = p2.x; wv[o][5] = p2.y; wv[o][6] = p3.x; wv[o][7] = p3.y;
+      }
+    }
+    constexpr int PU = 4;   // pixels in flight per warp (all loads issued before the first use)
+    for (long long pix0 = warp0 * PU; pix0 < npix; pix0 += nwarps * PU) {
+      uint4 xr[PU];
+      float gd[PU][kMaxCo], fr[PU][kMaxCo], cout_s[PU];
 #pragma unroll
-      for (int o = 0; o < kMaxCo; ++o) {
-        gf[o] = 0.f;
-        if (o < a.Co) {
-          const size_t oi = ((size_t)b * a.Co + o) * a.HW + p;
-          const float gd = a.g_D[oi] * c_out;
-          if (cc == 0 && lane == 0) dgain += gd * a.f_raw[oi];
-          gf[o] = gd * gain_out;
+      for (int u = 0; u < PU; ++u) {
+        const long long pix = pix0 + u;
+        cout_s[u] = 0.f;
+#pragma unroll
+        for (int o = 0; o < kMaxCo; ++o) { gd[u][o] = 0.f; fr[u][o] = 0.f; }
+        if (pix < npix) {
+          const int b = (int)(pix / a.HW);
+          const int p = (int)(pix - (long long)b * a.HW);
+          const float s = a.sigma[b * a.sigma_stride];
+          cout_s[u] = s * sd * rsqrtf(s * s + sd * sd);
+#pragma unroll
+          for (int o = 0; o < kMaxCo; ++o)
+            if (o < a.Co) {
+              const size_t oi = ((size_t)b * a.Co + o) * a.HW + p;
+              gd[u][o] = a.g_D[oi];
+              if (cg0 == 0 && lane == 0) fr[u][o] = a.f_raw[oi];
+            }
+          if (on) xr[u] = *reinterpret_cast<const uint4*>(a.x + pix * a.C + cg * 8);
         }
       }
-      const int c0 = lane * per_lane + cc;
-      for (int i = 0; i < nch; ++i) {
-        const float xv = __bfloat162float(a.x[pix * a.C + c0 + i]);
-        float gx = 0.f;
 #pragma unroll
-        for (int o = 0; o < kMaxCo; ++o)
-          if (o < a.Co) {
-            dw[o][i] += gf[o] * xv;
-            gx += gf[o] * __bfloat162float(a.w[(size_t)o * a.C + c0 + i]);
+      for (int u = 0; u < PU; ++u) {
+        const long long pix = pix0 + u;
+        if (pix < npix) {
+          float gf[kMaxCo];
+#pragma unroll
+          for (int o = 0; o < kMaxCo; ++o) {
+            const float g1 = gd[u][o] * cout_s[u];
+            dgain += g1 * fr[u][o];
+            gf[o] = g1 * gain_out;
           }
-        a.g_x[pix * a.C + c0 + i] = __float2bfloat16_rn(gx);
+          if (on) {
+            const uint4 uu = xr[u];
+            const float2 p0 = unpack_bf16(uu.x), p1 = unpack_bf16(uu.y), p2 = unpack_bf16(uu.z), p3 = unpack_bf16(uu.w);
+            const float xv[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+            float gx[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float t = 0.f;
+#pragma unroll
+              for (int o = 0; o < kMaxCo; ++o) {
+                t += gf[o] * wv[o][i];
+                dw[o][i] += gf[o] * xv[i];
+              }
+              gx[i] = t;
+            }
+            uint4 o4;
+            o4.x = pack_bf16(gx[0], gx[1]); o4.y = pack_bf16(gx[2], gx[3]); o4.z = pack_bf16(gx[4], gx[5]); o4.w = pack_bf16(gx[6], gx[7]);
+            *reinterpret_cast<uint4*>(a.g_x + pix * a.C + cg * 8) = o4;
+          }
+        }
       }
     }
-    // block reduction of dw over warps, then atomics
-    for (int o = 0; o < a.Co; ++o)
-      for (int i = 0; i < nch; ++i) sm[(size_t)wib * a.Co * a.C + (size_t)o * a.C + lane * per_lane + cc + i] = dw[o][i];
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < a.Co * a.C; idx += blockDim.x) {
-      const int c = idx % a.C;
-      const int lc = c % per_lane;
-      if (lc >= cc && lc < cc + nch) {
-        float t = 0.f;
-        for (int w2 = 0; w2 < nw; ++w2) t += sm[(size_t)w2 * a.Co * a.C + idx];
-        atomicAdd(a.g_w + idx, t);
-      }
+    if (on) {
+      for (int o = 0; o < a.Co; ++o)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sm[(size_t)wib * a.Co * a.C + (size_t)o * a.C + cg * 8 + i] = dw[o][i];
     }
-    __syncthreads();
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < a.Co * a.C; idx += blockDim.x) {
+    float t = 0.f;
+    for (int w2 = 0; w2 < nw; ++w2) t += sm[(size_t)w2 * a.Co * a.C + idx];
+    atomicAdd(a.g_w + idx, t);
   }
   dgain = warp_sum(dgain);
   if (lane == 0 && dgain != 0.f) atomicAdd(a.g_gain_out, dgain);
@@ -579,7 +619,8 @@ int mod_finish_forward(const float* lin, const float* const* gains, const int* c
 }
 int mod_finish_backward(const float* lin, const float* dm, const float* const* gains, const int* blk_start, float* d_lin,
                         float* d_gain, int B, int N, int n_blocks, cudaStream_t stream) {
-  mod_finish_bwd_kernel<<<n_blocks, 256, 0, stream>>>(lin, dm, gains, blk_start, d_lin, d_gain, B, N);
+  dim3 grid(n_blocks, B < 32 ? (B < 1 ? 1 : B) : 32);
+  mod_finish_bwd_kernel<<<grid, 256, 0, stream>>>(lin, dm, gains, blk_start, d_lin, d_gain, B, N);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
@@ -623,7 +664,7 @@ int conv_out_backward(const ConvOutBwdArgs& a, cudaStream_t stream) {
   TEDM_CHECK(a.Co >= 1 && a.Co <= kMaxCo && a.C % 64 == 0, "conv_out_bwd: unsupported Co=%d C=%d", a.Co, a.C);
   const long long npix = (long long)a.B * a.HW;
   long long blocks = (npix + 63) / 64;  // >= 8 pixels per warp
-  if (blocks > 2 * num_sms()) blocks = 2 * num_sms();
+  if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
   if (blocks < 1) blocks = 1;
   const size_t smem = (size_t)8 * a.Co * a.C * sizeof(float);
   TEDM_CHECK(smem <= 48 * 1024, "conv_out_bwd: C too large");

@@ -130,6 +130,12 @@ class EDM(_Base):
         _, embedding = self.embedding(sigma, class_label)
         return self.denoiser(noisy_image, sigma, embedding)
 
+    def prepare_weights(self, device) -> None:
+        """Refreshes the cached normalised weights of the embedding and the denoiser (no-op while they are current);
+        lets `DeterministicSolver` replay its CUDA graph after the parameters were updated or swapped with the EMA."""
+        self.embedding.prepare_weights(device)
+        self.denoiser.prepare_weights(device)
+
     def predict_step(self, batch, batch_idx: int, dataloader_idx: int | None = None):
         """edm.py:288-295."""
         x0, class_label = batch

@@ -82,6 +82,8 @@ class WeightBank:
         self._table_ptrs = None
         self._have_grad_buffers = False
         self.total_rows = sum(s.rows for s in slots)
+        self.total_groups = sum((s.rows + 15) // 16 for s in slots)     # 16 prepared rows per CTA of weight_prep_fwd
+        self.max_row_floats = max(s.taps * (s.cin + 1) for s in slots)  # staging of one dL/dw_hat row in weight_prep_bwd
 
     # ---- buffers ----
     def materialise(self, device: torch.device) -> None:
@@ -167,7 +169,10 @@ class WeightBank:
 
     def _build_table(self) -> None:
         arr = (_lib.WeightDesc * len(self.slots))()
+        group = 0
         for d, s in zip(arr, self.slots):
+            d.group_start = group
+            group += (s.rows + 15) // 16
             p = s.param
             if not (p.is_cuda and p.dtype == F32 and p.is_contiguous()):
                 raise RuntimeError(f"tinyedm_b200: parameter {s.name} must be a contiguous fp32 CUDA tensor")
@@ -193,14 +198,14 @@ class WeightBank:
             self._build_table()
             self._key = None
         if training:
-            ops.weight_prep_forward(self._table, len(self.slots), self.total_rows, True)
+            ops.weight_prep_forward(self._table, len(self.slots), self.total_groups, True)
             # the kernel rewrote every parameter in place (networks.py:32-34): let autograd / EMA code see the mutation
             torch.autograd.graph.increment_version([s.param for s in self.slots])
             self._key = None
             return
         key = tuple(s.param._version for s in self.slots)
         if key != self._key:
-            ops.weight_prep_forward(self._table, len(self.slots), self.total_rows, False)
+            ops.weight_prep_forward(self._table, len(self.slots), self.total_groups, False)
             self._key = key
 
     def invalidate(self) -> None:
@@ -210,7 +215,7 @@ class WeightBank:
         """g_hat -> gradient of the raw parameter for every slot (one launch)."""
         if not self._table_current():
             self._build_table()
-        ops.weight_prep_backward(self._table, len(self.slots), self.total_rows)
+        ops.weight_prep_backward(self._table, len(self.slots), self.total_rows, self.max_row_floats)
 
 
 def conv_slot(name: str, param, *, dgrad: bool = True) -> WeightSlot:
@@ -510,7 +515,9 @@ class DenoiserEngine:
         sync = self.grad_sync
         if sync is not None:
             sync.backward_started()
-        self.s_out.ghat.zero_()
+        # ONE memset for every dL/dw_hat of the network; all weight-gradient kernels then accumulate (split-K partial
+        # sums via TMA reduce-add / atomics) instead of zeroing their own slice with 70+ small memsets
+        self.bank._ghat_flat.zero_()
         g = ops.conv_out_backward(g_D, ctx["f_raw"], ctx["x_last"], self.s_out.fwd, m.gain_out, sigma,
                                   float(m.sigma_data), self.s_out.ghat, sg[nb:])
         d_mod = torch.zeros((B, self.n_mod), device=dev, dtype=F32)
@@ -520,7 +527,7 @@ class DenoiserEngine:
             if sync is not None:
                 sync.unit_done()
         # conv_in weight gradient (its input is the image: no data gradient needed)
-        ops.conv2d_wgrad(g, ctx["xcol"], self.s_in.ghat, 1)
+        ops.conv2d_wgrad(g, ctx["xcol"], self.s_in.ghat, 1, accumulate=True)
         # modulation adjoint: d_mod -> block gains, embed weights, embedding
         d_lin = ops.mod_finish_backward(ctx["lin"], d_mod, self.gain_ptrs, self.blk_start, sg, nb)
         emb = ctx["emb"]
@@ -551,10 +558,10 @@ class DenoiserEngine:
     def _attn_backward(self, bp: BlockPlan, S: dict, g_out: Tensor) -> Tensor:
         c5 = 1.0 / math.sqrt(2.0)
         g_y = ops.conv2d(g_out, bp.w["out"].dgrad, 1, bp.cout, alpha=c5)
-        ops.conv2d_wgrad(g_out, S["y"], bp.w["out"].ghat, 1, alpha=c5)
+        ops.conv2d_wgrad(g_out, S["y"], bp.w["out"].ghat, 1, alpha=c5, accumulate=True)
         g_qkv = ops.attention_backward(S["qkv"], S["y"], g_y, S["lse"], self.m.num_heads)
         g_mid = ops.conv2d(g_qkv, bp.w["qkv"].dgrad, 1, bp.cout, epi=EPI_AXPBY, alpha=1.0, beta=c5, res=g_out)
-        ops.conv2d_wgrad(g_qkv, S["mid"], bp.w["qkv"].ghat, 1)
+        ops.conv2d_wgrad(g_qkv, S["mid"], bp.w["qkv"].ghat, 1, accumulate=True)
         return g_mid
 
     def _block_backward(self, bp: BlockPlan, S: dict, g_out: Tensor, ctx: dict, d_mod: Tensor, pending: dict) -> Tensor:
@@ -568,8 +575,8 @@ class DenoiserEngine:
         g_raw = ops.conv2d(g_mid, w2.dgrad, 3, bp.cout, epi=EPI_MODSILU_BWD, alpha=wb, aux=S["raw"], mod=ctx["mod"],
                            mod_off=bp.col0, d_mod=d_mod, drop_p=ctx["drop_p"], seed=0x5EED0000 + bp.index,
                            seed_ptr=self.step_counter)
-        ops.conv2d_wgrad(g_mid, S["h"], w2.ghat, 3, alpha=wb)
-        ops.conv2d_wgrad(g_raw, S["a"], w1.ghat, 3)
+        ops.conv2d_wgrad(g_mid, S["h"], w2.ghat, 3, alpha=wb, accumulate=True)
+        ops.conv2d_wgrad(g_raw, S["a"], w1.ghat, 3, accumulate=True)
         x = S["x"]
         if bp.kind == "enc":
             Hh, Ww = ops.resampled_hw(Hin, Win, bp.resample)
@@ -591,7 +598,7 @@ class DenoiserEngine:
                                         C1=bp.cout, C2=0, resample=RESAMPLE_NONE, pixelnorm=True)
             if has_1x1:
                 g_r = ops.conv2d(g_u, bp.w["conv_1x1"].dgrad, 1, bp.cin)
-                ops.conv2d_wgrad(g_u, S["r"], bp.w["conv_1x1"].ghat, 1)
+                ops.conv2d_wgrad(g_u, S["r"], bp.w["conv_1x1"].ghat, 1, accumulate=True)
             else:
                 g_r = g_u
             g_in, acc = self._take_g_in(bp, pending, (B, Hin, Win, bp.cin), dev)
@@ -605,7 +612,7 @@ class DenoiserEngine:
         ctot = bp.cin + bp.cskip
         if "conv_1x1" in bp.w:
             g_res = ops.conv2d(g_mid, bp.w["conv_1x1"].dgrad, 1, ctot, alpha=wa)
-            ops.conv2d_wgrad(g_mid, x, bp.w["conv_1x1"].ghat, 1, alpha=wa)
+            ops.conv2d_wgrad(g_mid, x, bp.w["conv_1x1"].ghat, 1, alpha=wa, accumulate=True)
             beta = 1.0
         else:
             g_res, beta = g_mid, wa

@@ -330,6 +330,10 @@ class Embedding(nn.Module):
             self._bank.materialise(dev)
         return self._bank
 
+    def prepare_weights(self, device) -> None:
+        """(Re)normalises the weights if a parameter changed since the last call (eval-mode cache refresh)."""
+        self._bank_for(torch.device(device)).prepare(self.training)
+
     def forward(self, sigmas, class_labels=None):
         if class_labels is not None and self.class_embed is None:
             raise ValueError("class_labels is not None, but num_classes is None. ")
@@ -534,6 +538,12 @@ class Denoiser(nn.Module):
             return _DenoiserFn.apply(noisy, sig, emb, self, *params)
         D, _ = self.engine.forward(noisy, sig, emb, training=self.training, save=False)
         return D
+
+    def prepare_weights(self, device) -> None:
+        """(Re)normalises the weights if a parameter changed since the last call (eval-mode cache refresh)."""
+        eng = self.engine
+        eng._ensure_device(torch.device(device))
+        eng.bank.prepare(self.training)
 
     def __getstate__(self):  # the engine holds device buffers and ctypes tables: rebuild lazily after copy/unpickle
         state = self.__dict__.copy()

@@ -53,12 +53,12 @@ def mp_add_coeffs(t: float) -> tuple[float, float]:
 # ---------------------------------------------------------------------------------------------------------
 # weight normalisation
 # ---------------------------------------------------------------------------------------------------------
-def weight_prep_forward(table: Tensor, n: int, total_rows: int, training: bool) -> None:
-    _lib.call("tedm_weight_prep_forward", table.data_ptr(), n, total_rows, 1 if training else 0, _stream())
+def weight_prep_forward(table: Tensor, n: int, total_groups: int, training: bool) -> None:
+    _lib.call("tedm_weight_prep_forward", table.data_ptr(), n, total_groups, 1 if training else 0, _stream())
 
 
-def weight_prep_backward(table: Tensor, n: int, total_rows: int) -> None:
-    _lib.call("tedm_weight_prep_backward", table.data_ptr(), n, total_rows, _stream())
+def weight_prep_backward(table: Tensor, n: int, total_rows: int, max_row_floats: int) -> None:
+    _lib.call("tedm_weight_prep_backward", table.data_ptr(), n, total_rows, max_row_floats, _stream())
 
 
 # ---------------------------------------------------------------------------------------------------------

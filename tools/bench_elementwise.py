@@ -1,0 +1,83 @@
+"""GB/s of the HBM-bound kernels at the CIFAR training shapes (B=256) against their ALGORITHMIC bytes
+(every distinct input read once + every output written once, storage dtype).
+Run under gpurun; writes gpurun_out/bench_elementwise.log. Peak: MEASURED_PEAKS.json hbm_gbs."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from tinyedm_b200 import ops
+from tinyedm_b200.ops import RESAMPLE_DOWN, RESAMPLE_NONE, RESAMPLE_UP
+
+os.makedirs("gpurun_out", exist_ok=True)
+log = open("gpurun_out/bench_elementwise.log", "w")
+def P(*a):
+    s = " ".join(str(x) for x in a); print(s, flush=True); log.write(s + "\n"); log.flush()
+dev = torch.device("cuda:0"); ops.ensure_device(dev); BF = torch.bfloat16; F32 = torch.float32
+try:
+    PEAK = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    PEAK = 6551.7
+flush_buf = torch.empty(256 << 20, device=dev, dtype=torch.uint8)   # > L2 (126 MB)
+
+def bench(fn, n=10):
+    for _ in range(2):
+        fn()
+    ts = []
+    for _ in range(n):
+        flush_buf.zero_()                       # evict the operands from L2 between iterations
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+def report(name, nbytes, fn):
+    t = bench(fn)
+    gbs = nbytes / t / 1e6
+    P(f"{name:58s} {nbytes/1e6:8.1f} MB {t*1e3:8.1f} us {gbs:8.1f} GB/s  {100*gbs/PEAK:5.1f}% of {PEAK:.0f}")
+
+B = int(os.environ.get("EW_B", 256))
+def rb(*shape): return torch.randn(*shape, device=dev).to(BF)
+for (H, C) in [(32, 256), (16, 256), (8, 256)]:
+    W = H
+    n = B * H * W * C * 2       # bytes of one (B,H,W,C) bf16 tensor
+    x = rb(B, H, W, C); s = rb(B, H, W, C); gain = torch.rand(B, C, device=dev)
+    a = torch.empty(100 << 20, device=dev); b_ = torch.empty_like(a)
+    report(f"[{H}x{H}] torch copy_ 100M fp32 (reference)", 800e6 * 1.048576, lambda: b_.copy_(a))
+    del a, b_
+    report(f"[{H}x{H}] block_prep fwd pixelnorm+silu (enc)  r C, w 2C", 3 * n, lambda: ops.block_prep(x, pixelnorm=True, want_nrm=True))
+    report(f"[{H}x{H}] block_prep fwd silu only (dec)       r C, w C", 2 * n, lambda: ops.block_prep(x, want_x=False))
+    report(f"[{H}x{H}] block_prep fwd concat*gain+silu      r 2C, w 4C", 6 * n, lambda: ops.block_prep(x, skip=s, gain=gain))
+    if H > 8:
+        report(f"[{H}x{H}] block_prep fwd down+pixelnorm+silu   r C, w C/2", 1.5 * n, lambda: ops.block_prep(x, resample=RESAMPLE_DOWN, pixelnorm=True, want_nrm=True))
+    if H < 32:
+        report(f"[{H}x{H}] block_prep fwd up+silu               r C, w 8C", 9 * n, lambda: ops.block_prep(x, resample=RESAMPLE_UP))
+    # backward: split of the concatenated gradient (+ ScaleLong mean-gradient, accumulate into a pending skip gradient)
+    gcat = rb(B, H, W, 2 * C); g_in = rb(B, H, W, C); g_skip = torch.empty(B, H, W, C, device=dev, dtype=BF)
+    d_mean = torch.randn(B, C, device=dev)
+    kw = dict(g_res=gcat, beta=1.0, g_a=None, x=None, nrm=None, gain=gain, d_mean=d_mean, g_in=g_in, g_skip=g_skip,
+              accumulate_skip=False, B=B, Hin=H, Win=W, C1=C, C2=C, resample=RESAMPLE_NONE, pixelnorm=False)
+    report(f"[{H}x{H}] block_prep bwd split                 r 2C, w 2C", 4 * n, lambda: ops.block_prep_backward(accumulate_in=False, **kw))
+    report(f"[{H}x{H}] block_prep bwd split (+= into g_in)  r 3C, w 2C", 5 * n, lambda: ops.block_prep_backward(accumulate_in=True, **kw))
+    mean = torch.zeros(B, C, device=dev)
+    report(f"[{H}x{H}] channel_dot mean (ScaleLong input)   r C", n, lambda: ops.channel_dot(s, None, mean, C, 0, 1.0 / (H * W)))
+    report(f"[{H}x{H}] channel_dot gain gradient            r 2C", 2 * n, lambda: ops.channel_dot(gcat, s, mean, C, C, 1.0))
+    if H < 32:
+        gx = rb(B, 2 * H, 2 * W, C); gi = torch.empty(B, H, W, C, device=dev, dtype=BF)
+        kw2 = dict(g_res=gx, beta=1.0, g_a=None, x=None, nrm=None, gain=None, d_mean=None, g_in=gi, g_skip=None,
+                   accumulate_in=False, accumulate_skip=False, B=B, Hin=H, Win=W, C1=C, C2=0, resample=RESAMPLE_UP, pixelnorm=False)
+        report(f"[{H}x{H}] block_prep bwd adjoint of upsample   r 4C, w C", 5 * n, lambda: ops.block_prep_backward(**kw2))
+    del x, s, gcat, g_in, g_skip
+
+# image-sized and parameter-sized kernels
+from tinyedm_b200 import configs
+from tinyedm_b200.networks import Denoiser
+den = Denoiser(**configs.CIFAR10["denoiser"]).to(dev)
+if den is not None:
+    eng = den.engine
+    eng._ensure_device(dev)
+    bank = eng.bank
+    Pn = sum(s.param.numel() for s in bank.slots)
+    bank.ensure_grad_buffers()
+    report("weight_prep fwd (train: rewrite + 2 bf16 layouts)  r 4P, w 4P+2P+2P", 12 * Pn, lambda: (bank.invalidate(), bank.prepare(True)))
+    report("weight_prep fwd (eval)                           r 4P, w 2P+2P", 8 * Pn, lambda: (bank.invalidate(), bank._build_table() if bank._table is None else None, ops.weight_prep_forward(bank._table, len(bank.slots), bank.total_groups, False)))
+    report("weight_prep bwd                                  r 4P+4P, w 4P", 12 * Pn, lambda: bank.backward())
