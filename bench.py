@@ -29,7 +29,7 @@ TRAIN_BATCH = 256
 SAMPLE_BATCH = 128
 SAMPLE_STEPS = 32
 FWD_GFLOP_PER_IMG = 27.001          # BASELINE.md §2 (conv3x3 24.707 + conv1x1 1.931 + attention 0.361 + linear)
-# dominant kernel: conv_gemm_kernel<256>, 3x3 256->256 at 32x32, per-GPU batch 256
+# dominant kernel: conv_pair_kernel, 3x3 256->256 at 32x32, per-GPU batch 256
 DOM = dict(B=TRAIN_BATCH, H=32, W=32, Cin=256, Cout=256, k=3)
 DOM_FLOP = 2.0 * DOM["B"] * DOM["H"] * DOM["W"] * DOM["Cin"] * DOM["Cout"] * DOM["k"] ** 2
 
@@ -331,8 +331,8 @@ def run_b200(args) -> None:
         by_epi.setdefault(e, []).append(a.elapsed_time(b))
     per_flavour = {flavour.get(e, str(e)): {"launches": len(v), "ms_avg": sum(v) / len(v),
                                             "tflops": DOM_FLOP / (sum(v) / len(v) * 1e-3) / 1e12} for e, v in sorted(by_epi.items())}
-    roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel<256,*> 3x3 256->256 @32x32 B256, every launch of this shape in a "
-                "training step (forward and data-gradient, with their fused epilogues)",
+    roofline = {"bound": "tensor", "kernel": "conv_pair_kernel<*> (tcgen05 cta_group::2 implicit GEMM) 3x3 256->256 @32x32 B256, every "
+                "launch of this shape in a training step (forward and data-gradient, with their fused epilogues)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if pk else "fallback (B200_PROFILING.md)",
                 "launch_ms_avg": dom_avg, "launches_timed": len(dom_ms), "traffic": TRAFFIC_BYTES,
@@ -405,9 +405,10 @@ def run_b200(args) -> None:
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full`
-# capture (profiles/); None until one exists for the current kernel.
-TRAFFIC_BYTES = None
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (conv_pair_kernel, 3x3 256->256 @32x32,
+# B=256) from the committed `ncu --set full` capture profiles/r1h_conv_pair_ncu_full.md: mean of the two captured
+# flavours (modulation-silu 347.8 MB, mp_add 376.8 MB); algorithmic bytes are 402-403 MB per launch.
+TRAFFIC_BYTES = 362.3e6
 
 
 def main() -> None:

@@ -1,0 +1,57 @@
+"""Cosine attention kernels (tcgen05 forward for hd=64 / S in {64,256}; warp-MMA kernels otherwise and for the backward)
+against CosineAttention.forward's arithmetic (src/tinyedm/networks.py:194-202) in fp32 torch."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.helpers import rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def reference(qkv: torch.Tensor, heads: int):
+    """qkv (B,S,3C) with channel = {q,k,v}*C + head*hd + d  ->  y (B,S,C), fp32, differentiable w.r.t. qkv."""
+    B, S, C3 = qkv.shape
+    C = C3 // 3
+    hd = C // heads
+    t = qkv.view(B, S, 3, heads, hd).permute(2, 0, 3, 1, 4)                  # (3,B,heads,S,hd)
+    n = t.norm(dim=-1, keepdim=True) / math.sqrt(hd)
+    t = t / (1e-4 + n)                                                        # pixel_norm over hd (networks.py:9-14)
+    y = F.scaled_dot_product_attention(t[0], t[1], t[2])                      # (B,heads,S,hd), scale 1/sqrt(hd)
+    return y.permute(0, 2, 1, 3).reshape(B, S, C)
+
+
+@pytest.mark.parametrize("B,H,W,heads,hd", [(3, 16, 16, 4, 64), (5, 8, 8, 4, 64), (3, 8, 8, 3, 64), (1, 8, 8, 1, 64),
+                                            (2, 14, 14, 4, 64), (2, 7, 7, 4, 128), (2, 16, 16, 4, 144)])
+def test_attention_forward_backward_vs_torch(dev, B, H, W, heads, hd):
+    from tinyedm_b200 import ops
+    ops.ensure_device(dev)
+    torch.manual_seed(B * 1000 + H * 10 + heads)
+    C = heads * hd
+    qkv = (torch.randn(B, H, W, 3 * C, device=dev) * 1.3).to(torch.bfloat16)
+    y, lse = ops.attention_forward(qkv, heads, need_lse=True)
+    x = qkv.float().view(B, H * W, 3 * C).requires_grad_(True)
+    with torch.backends.cuda.sdp_kernel(enable_flash=False, enable_mem_efficient=False, enable_math=True):
+        ref = reference(x, heads)
+    r = rel(y.view(B, H * W, C), ref)
+    assert r < 1e-2, r                                    # north_star: bf16 per-layer relative L2 <= 1e-2
+    assert torch.isfinite(lse).all()
+    # log-sum-exp of the scaled scores of the normalised q, k
+    t = x.detach().view(B, H * W, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    t = t / (1e-4 + t.norm(dim=-1, keepdim=True) / math.sqrt(hd))
+    lse_ref = torch.logsumexp(t[0] @ t[1].transpose(-1, -2) / math.sqrt(hd), dim=-1)    # (B,heads,S)
+    assert rel(lse.view(B, heads, H * W), lse_ref) < 2e-3
+    g_y = torch.randn(B, H, W, C, device=dev).to(torch.bfloat16)
+    g_qkv = ops.attention_backward(qkv, y, g_y, lse, heads)
+    (g_ref,) = torch.autograd.grad(ref, x, g_y.float().view(B, H * W, C))
+    rg = rel(g_qkv.view(B, H * W, 3 * C), g_ref)
+    assert rg < 3e-2, rg

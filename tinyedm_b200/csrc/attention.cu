@@ -18,6 +18,8 @@
 //
 // This 1.3%-of-FLOPs op stays on the warp-level tensor path in round 1 (problem per head is 256x256x64: too
 // small to amortise a tcgen05/TMEM pipeline without batching heads per CTA); see DESIGN.md.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -573,6 +575,8 @@ int launch_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* y, const __nv_bflo
 int attention_forward(const __nv_bfloat16* qkv, __nv_bfloat16* y, float* lse, int B, int S, int heads, int hd,
                       cudaStream_t stream) {
   if (check_dims(S, hd, heads) != 0) return -1;
+  static const bool use_tc = [] { const char* e = getenv("TEDM_ATTN_TC"); return !(e != nullptr && e[0] == '0'); }();
+  if (use_tc && attention_tc_supported(S, hd)) return attention_forward_tc(qkv, y, lse, B, S, heads, stream);
   switch (hd) {
     case 32: return launch_fwd<32>(qkv, y, lse, B, S, heads, stream);
     case 64: return launch_fwd<64>(qkv, y, lse, B, S, heads, stream);

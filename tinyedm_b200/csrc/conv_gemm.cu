@@ -482,7 +482,9 @@ static int conv_pair_mode() {
 
 int conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t stream) {
   TEDM_CHECK(a.ksize == 1 || a.ksize == 3, "conv_gemm: kernel size must be 1 or 3 (got %d)", a.ksize);
-  if (a.block_n_override == 0 && conv_pair_mode() == 1 && a.B > 0 && conv_pair_supported(a)) return conv_pair_launch(a, stream);
+  if (a.block_n_override == 0 && conv_pair_mode() == 1 && a.B > 0 && conv_pair_supported(a) &&
+      (a.nrm != nullptr || 4 * conv_pair_tiles(a) > num_sms()))   // at least half of the CTA pairs get a tile
+    return conv_pair_launch(a, stream);
   TEDM_CHECK(a.Cin % 64 == 0, "conv_gemm: Cin must be a multiple of 64 (got %d)", a.Cin);
   TEDM_CHECK(a.Cout % 16 == 0 && a.Cout >= 16, "conv_gemm: Cout must be a multiple of 16 (got %d)", a.Cout);
   TEDM_CHECK(a.B > 0 && a.H > 0 && a.W > 0, "conv_gemm: empty input");

@@ -13,7 +13,7 @@
 //     store; each thread touches only its own 128-byte row of a swizzled buffer (conflict-free 16-byte accesses).
 //
 // Roles per CTA (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM
-// allocator, warps 4..11 = epilogue (4 TMEM lane quarters x 2 column halves). Accumulators are double buffered in
+// allocator, warps 4..11 = epilogue (4 TMEM lane quarters x 2 column halves [x kSub warps per 64-column chunk]). Accumulators are double buffered in
 // TMEM (2 x 256 columns in each CTA).
 #include <mutex>
 
@@ -33,8 +33,15 @@ constexpr int kStageBytes = kATileBytes + kBHalfBytes;
 constexpr int kStages = 4;
 constexpr int kEpiBufBytes = kBM * 128;               // 128 pixels x 64 channels bf16
 constexpr int kEpiBufsPerHalf = 3;
-constexpr int kThreads = 384;
-constexpr int kEpiWarps = 8;
+// Epilogue warps sharing a (TMEM lane quarter, column half); each owns 64/kSub columns of a chunk. kSub = 2 (16 epilogue
+// warps, 16-column register steps) was measured on B200: no faster than kSub = 1 — under the power cap the extra warps buy
+// nothing because the epilogue already overlaps the next tile's main loop — and slower for the two-sweep variant.
+constexpr int kSub = 1;
+constexpr int kEpiWarps = 8 * kSub;
+constexpr int kThreads = 128 + 32 * kEpiWarps;        // 384 (640 with kSub = 2)
+constexpr int kHalfThreads = 128 * kSub;              // threads behind one named barrier / one set of staging buffers
+constexpr int CW = kSub == 1 ? 32 : 16;               // columns per register step (640 threads would leave <= 102 registers each)
+constexpr int kStepsPerWarp = 64 / kSub / CW;
 constexpr int kTmemCols = 512;
 constexpr int kOffEpi = kStages * kStageBytes;
 constexpr int kOffBars = kOffEpi + 2 * kEpiBufsPerHalf * kEpiBufBytes;
@@ -68,18 +75,20 @@ __device__ __forceinline__ MTile decode_m(const ConvGemmParams& p, int mt) {
 __device__ __forceinline__ uint4* srow(uint8_t* buf, int m, int j) {
   return reinterpret_cast<uint4*>(buf + m * 128 + ((j ^ (m & 7)) << 4));
 }
-__device__ __forceinline__ void srow_load32(uint8_t* buf, int m, int j0, float (&f)[32]) {
+template <int N>
+__device__ __forceinline__ void srow_load(uint8_t* buf, int m, int j0, float (&f)[N]) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
+  for (int g = 0; g < N / 8; ++g) {
     const uint4 u = *srow(buf, m, j0 + g);
     const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
     f[g * 8 + 0] = a.x; f[g * 8 + 1] = a.y; f[g * 8 + 2] = b.x; f[g * 8 + 3] = b.y;
     f[g * 8 + 4] = c.x; f[g * 8 + 5] = c.y; f[g * 8 + 6] = d.x; f[g * 8 + 7] = d.y;
   }
 }
-__device__ __forceinline__ void srow_store32(uint8_t* buf, int m, int j0, const float (&v)[32]) {
+template <int N>
+__device__ __forceinline__ void srow_store(uint8_t* buf, int m, int j0, const float (&v)[N]) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
+  for (int g = 0; g < N / 8; ++g) {
     uint4 o;
     o.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
     o.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
@@ -89,10 +98,12 @@ __device__ __forceinline__ void srow_store32(uint8_t* buf, int m, int j0, const 
   }
 }
 
-// 32 values per lane -> lane j ends up with the sum over all 32 lanes of value j (31 shuffles)
-__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
+// N values per lane (N = 16 or 32) -> lane j < N ends up with the sum over all 32 lanes of value j (N - 1 exchange
+// shuffles, + 1 for N = 16 where lanes j and j + 16 hold the two halves of column j)
+template <int N>
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[N], int lane) {
 #pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
+  for (int s = N / 2; s >= 1; s >>= 1) {
     const bool up = (lane & s) != 0;
 #pragma unroll
     for (int i = 0; i < s; ++i) {
@@ -101,19 +112,26 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lan
       v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
     }
   }
+  if (N == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
   return v[0];
 }
 
-__device__ __forceinline__ void dropout_apply32(float (&v)[32], unsigned long long e0, float drop_p, uint32_t dseed) {
+template <int N>
+__device__ __forceinline__ void dropout_apply(float (&v)[N], unsigned long long e0, float drop_p, uint32_t dseed) {
   const float keep_scale = 1.0f / (1.0f - drop_p);
   const uint32_t thresh = (uint32_t)(drop_p * 65536.0f);
 #pragma unroll
-  for (int i = 0; i < 32; i += 2) {
+  for (int i = 0; i < N; i += 2) {
     const uint32_t bits = dropout_bits2(e0 + i, dseed);
     v[i] = (bits & 0xFFFFu) >= thresh ? v[i] * keep_scale : 0.f;
     v[i + 1] = (bits >> 16) >= thresh ? v[i + 1] * keep_scale : 0.f;
   }
 }
+
+__device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
+__device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
+__device__ __forceinline__ void tmem_st_cw(uint32_t taddr, const uint32_t (&r)[16]) { tmem_st16(taddr, r); }
+__device__ __forceinline__ void tmem_st_cw(uint32_t taddr, const uint32_t (&r)[32]) { tmem_st32(taddr, r); }
 
 // Position of one epilogue half (4 warps) in its stream of 64-channel chunks.
 struct ChunkPos {
@@ -244,9 +262,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;               // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;     // which half of the tile's 64-channel chunks this warp works on
+    const int half = (warp - 4) / (4 * kSub);       // which half of the tile's 64-channel chunks this warp works on
+    const int sub = ((warp - 4) >> 2) % kSub;       // which 64/kSub columns of a chunk this warp owns
     const int m = q * 32 + lane;          // accumulator row == pixel within this CTA's tile
-    const bool elected = (warp == 4 + 4 * half) && lane == 0;
+    const bool elected = (warp == 4 + 4 * kSub * half) && lane == 0;
     const int bar_half = 1 + half;        // named barrier of this half (128 threads)
     const int rows_in_tile = p.NB * p.RH * p.W;
     const uint32_t box_bytes = (uint32_t)rows_in_tile * 128;
@@ -362,7 +381,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const bool writes_out = !sweep1;
         if (top_barrier && writes_out) {
           if (elected) bulk_wait_read0();
-          named_bar_sync(bar_half, 128);
+          named_bar_sync(bar_half, kHalfThreads);
         }
         if (kHasIn) {
           mbar_wait_bounded(my_in_full, in_phase);
@@ -371,54 +390,55 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint8_t* obuf = (EPI == EPI_PLAIN) ? ((qi & 1) ? buf1 : buf0)
                         : (kPingPong ? ((qi & 1) ? buf2 : buf1) : (EPI == EPI_MODSILU ? buf1 : buf2));
 #pragma unroll 1
-        for (int s = 0; s < 2; ++s) {
-          const int cc = pos.c * 64 + s * 32;   // first column of this step within the tile
-          const int j0 = s * 4;
-          uint32_t r[32];
-          tmem_ld32(t_row + cc, r);
+        for (int s = 0; s < kStepsPerWarp; ++s) {
+          const int col_in_chunk = sub * (64 / kSub) + s * CW;
+          const int cc = pos.c * 64 + col_in_chunk;   // first column of this step within the tile
+          const int j0 = col_in_chunk / 8;
+          uint32_t r[CW];
+          tmem_ld_cw(t_row + cc, r);
           tmem_ld_wait();
-          float v[32];
+          float v[CW];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+          for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
           if constexpr (EPI == EPI_PLAIN) {
-            if (row_ok) srow_store32(obuf, m, j0, v);
+            if (row_ok) srow_store<CW>(obuf, m, j0, v);
           } else if constexpr (EPI == EPI_MODSILU) {
             // the reference's conv output is bf16 before the fp32 modulation island (networks.py:253-258)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
+            for (int i = 0; i < CW; ++i) v[i] = bf16_round(v[i]);
             if (row_ok) {
-              if (p.out2 != nullptr) srow_store32(buf0, m, j0, v);
+              if (p.out2 != nullptr) srow_store<CW>(buf0, m, j0, v);
               const float* mrow = p.mod + (long long)b * p.mod_stride + n0 + cc;
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
+              for (int g = 0; g < CW / 4; ++g) {
                 const float4 mm = *reinterpret_cast<const float4*>(mrow + g * 4);
                 v[g * 4 + 0] = mp_silu_f(v[g * 4 + 0] * mm.x);
                 v[g * 4 + 1] = mp_silu_f(v[g * 4 + 1] * mm.y);
                 v[g * 4 + 2] = mp_silu_f(v[g * 4 + 2] * mm.z);
                 v[g * 4 + 3] = mp_silu_f(v[g * 4 + 3] * mm.w);
               }
-              if (p.drop_p > 0.f) dropout_apply32(v, (unsigned long long)pix * p.Cout + n0 + cc, p.drop_p, dseed);
-              srow_store32(buf1, m, j0, v);
+              if (p.drop_p > 0.f) dropout_apply<CW>(v, (unsigned long long)pix * p.Cout + n0 + cc, p.drop_p, dseed);
+              srow_store<CW>(buf1, m, j0, v);
             }
           } else if constexpr (EPI == EPI_AXPBY) {
             if (row_ok) {
-              float rv[32];
-              srow_load32(buf0, m, j0, rv);
+              float rv[CW];
+              srow_load<CW>(buf0, m, j0, rv);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] += p.beta * rv[i];
-              srow_store32(obuf, m, j0, v);
+              for (int i = 0; i < CW; ++i) v[i] += p.beta * rv[i];
+              srow_store<CW>(obuf, m, j0, v);
             }
           } else if constexpr (EPI == EPI_MODSILU_BWD) {
             // backward of h = drop(mp_silu(raw * m)):  gz = g_h * keep/(1-p) * mp_silu'(raw*m);  g_raw = gz * m;
             // d_mod[b,c] += sum_pixels gz * raw
-            float dm[32];
+            float dm[CW];
             if (valid) {
-              float rw[32];
-              srow_load32(buf0, m, j0, rw);
+              float rw[CW];
+              srow_load<CW>(buf0, m, j0, rw);
               const float* mrow = p.mod + (long long)b * p.mod_stride + n0 + cc;
-              if (p.drop_p > 0.f) dropout_apply32(v, (unsigned long long)pix * p.Cout + n0 + cc, p.drop_p, dseed);
+              if (p.drop_p > 0.f) dropout_apply<CW>(v, (unsigned long long)pix * p.Cout + n0 + cc, p.drop_p, dseed);
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
+              for (int g = 0; g < CW / 4; ++g) {
                 const float4 mm = *reinterpret_cast<const float4*>(mrow + g * 4);
                 const float mv[4] = {mm.x, mm.y, mm.z, mm.w};
 #pragma unroll
@@ -431,63 +451,63 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) { dm[i] = 0.f; v[i] = 0.f; }
+              for (int i = 0; i < CW; ++i) { dm[i] = 0.f; v[i] = 0.f; }
             }
-            if (row_ok) srow_store32(obuf, m, j0, v);
+            if (row_ok) srow_store<CW>(obuf, m, j0, v);
             if (warp_one_image) {
               const long long pw = t.p_base + q * 32;   // first pixel of this warp's rows
-              const float tot = warp_transpose_reduce32(dm, lane);
-              if (q * 32 < rows_in_tile && pw < t.p_limit && cc + lane < n_this)
+              const float tot = warp_transpose_reduce<CW>(dm, lane);
+              if (q * 32 < rows_in_tile && pw < t.p_limit && lane < CW && cc + lane < n_this)
                 atomicAdd(p.d_mod + (long long)(pw / HW) * p.mod_stride + n0 + cc + lane, tot);
             } else if (valid) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
+              for (int i = 0; i < CW; ++i)
                 if (cc + i < n_this) atomicAdd(p.d_mod + (long long)b * p.mod_stride + n0 + cc + i, dm[i]);
             }
           } else if constexpr (EPI == EPI_SILU_BWD) {
             // g_x = alpha*acc * mp_silu'(x) + beta*res, [pixel-norm adjoint: g/n - x*dot/((n-eps) n C)], (+ old out)
-            float xv[32];
-            if (row_ok) srow_load32(buf0, m, j0, xv);
+            float xv[CW];
+            if (row_ok) srow_load<CW>(buf0, m, j0, xv);
             else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) xv[i] = 0.f;
+              for (int i = 0; i < CW; ++i) xv[i] = 0.f;
             }
             if (two_sweep && pos.pass == 1) {
               // v was parked in TMEM by the first sweep
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * inv_n - xv[i] * kk;
+              for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]) * inv_n - xv[i] * kk;
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] *= mp_silu_grad_f(xv[i]);
+              for (int i = 0; i < CW; ++i) v[i] *= mp_silu_grad_f(xv[i]);
               if (use_res && row_ok) {
-                float rv[32];
-                srow_load32(buf1, m, j0, rv);
+                float rv[CW];
+                srow_load<CW>(buf1, m, j0, rv);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += p.beta * rv[i];
+                for (int i = 0; i < CW; ++i) v[i] += p.beta * rv[i];
               }
             }
             if (sweep1) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
+              for (int i = 0; i < CW; ++i) {
                 dot += v[i] * xv[i];
                 r[i] = __float_as_uint(v[i]);
               }
-              tmem_st32(t_row + cc, r);
+              tmem_st_cw(t_row + cc, r);
             } else if (row_ok) {
               if (use_old) {
-                float ov[32];
-                srow_load32(buf2, m, j0, ov);
+                float ov[CW];
+                srow_load<CW>(buf2, m, j0, ov);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += ov[i];
+                for (int i = 0; i < CW; ++i) v[i] += ov[i];
               }
-              srow_store32(buf2, m, j0, v);
+              srow_store<CW>(buf2, m, j0, v);
             }
           }
         }
         if (sweep1) tmem_st_wait();
         if (writes_out) fence_proxy_async_smem();
         if (kPingPong && elected) bulk_wait_read0();   // the store issued one chunk ago has released the other buffer
-        named_bar_sync(bar_half, 128);
+        named_bar_sync(bar_half, kHalfThreads);
         ChunkPos nx = pos;
         advance(nx);
         if (elected) {
@@ -506,10 +526,18 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         ++qi;
         // end of the first sweep over this half's chunks: combine the two halves' partial dots of each row
         if (sweep1 && pos.c + 1 == pos.ce) {
-          row_dots[half * 128 + m] = dot;
-          named_bar_sync(3 + q, 64);
+          // 2 * kSub warps hold partial dots of the same 32 rows: first the sub-warps of a half combine, then the halves
+          float tot = dot;
+          for (int w2 = kSub - 1; w2 >= 1; --w2) {
+            if (sub == w2) row_dots[half * 128 + m] = tot;
+            named_bar_sync(3 + q, 64 * kSub);
+            if (sub == w2 - 1) tot += row_dots[half * 128 + m];
+            named_bar_sync(3 + q, 64 * kSub);
+          }
+          if (sub == 0) row_dots[half * 128 + m] = tot;
+          named_bar_sync(3 + q, 64 * kSub);
           const float d2 = row_dots[m] + row_dots[128 + m];
-          named_bar_sync(3 + q, 64);
+          named_bar_sync(3 + q, 64 * kSub);
           const float n = valid ? p.nrm[pix] : 1.0f;
           inv_n = 1.0f / n;
           kk = d2 / (fmaxf(n - 1e-4f, 1e-20f) * (float)p.Cout);
@@ -518,9 +546,13 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       } else {
         // this half has no chunk in this tile (64-channel tile): with two_sweep its dot share is zero
         if (two_sweep) {
-          row_dots[half * 128 + m] = 0.f;
-          named_bar_sync(3 + q, 64);
-          named_bar_sync(3 + q, 64);
+          for (int w2 = kSub - 1; w2 >= 1; --w2) {
+            named_bar_sync(3 + q, 64 * kSub);
+            named_bar_sync(3 + q, 64 * kSub);
+          }
+          if (sub == 0) row_dots[half * 128 + m] = 0.f;
+          named_bar_sync(3 + q, 64 * kSub);
+          named_bar_sync(3 + q, 64 * kSub);
         }
         advance(pos);
       }
@@ -636,6 +668,16 @@ bool conv_pair_supported(const ConvGemmArgs& a) {
   int RH, NB;
   if (conv_tile_geometry(a.H, a.W, &RH, &NB) != 0) return false;
   return true;
+}
+
+// Pair tiles (256 pixels x <=256 channels) of the problem: a launch that cannot occupy even half of the 74 CTA pairs is
+// better served by the single-CTA kernel's narrower tiles (shorter critical path per tile).
+int conv_pair_tiles(const ConvGemmArgs& a) {
+  int RH, NB;
+  if (conv_tile_geometry(a.H, a.W, &RH, &NB) != 0) return 0;
+  const int tiles_h = (a.H + RH - 1) / RH;
+  const int m_tiles = (NB == 1) ? a.B * tiles_h : (a.B + NB - 1) / NB;
+  return ((m_tiles + 1) / 2) * ((a.Cout + kBN - 1) / kBN);
 }
 
 int conv_pair_launch(const ConvGemmArgs& a, cudaStream_t stream) {

@@ -70,6 +70,7 @@ int conv_tile_geometry(int H, int W, int* RH, int* NB);
 int conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t stream);
 // conv_pair.cu: the CTA-pair (tcgen05 cta_group::2) version with the TMA-staged epilogue
 bool conv_pair_supported(const ConvGemmArgs& a);
+int conv_pair_tiles(const ConvGemmArgs& a);
 int conv_pair_launch(const ConvGemmArgs& a, cudaStream_t stream);
 
 struct ConvWgradArgs {
@@ -133,6 +134,10 @@ struct ChannelDotArgs {
   float scale;
 };
 int channel_dot(const ChannelDotArgs& a, cudaStream_t stream);
+
+// ---- attention_tc.cu: tcgen05/TMEM forward for head_dim 64, S in {64, 256} ----
+bool attention_tc_supported(int S, int hd);
+int attention_forward_tc(const __nv_bfloat16* qkv, __nv_bfloat16* y, float* lse, int B, int S, int heads, cudaStream_t stream);
 
 // ---- attention.cu ----
 int attention_forward(const __nv_bfloat16* qkv, __nv_bfloat16* y, float* lse, int B, int S, int heads, int hd,

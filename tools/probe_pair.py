@@ -31,7 +31,7 @@ def ref_conv(x, w):
     return F.conv2d(x.float().permute(0, 3, 1, 2), w.to(BF).float(), padding="same").permute(0, 2, 3, 1).contiguous()
 
 ok_all = True
-def check(name, new, old, tol=1e-6, ref=None, reftol=6e-3):
+def check(name, new, old, tol=1e-5, ref=None, reftol=6e-3):
     global ok_all
     torch.cuda.synchronize()
     r = rel(new, old)

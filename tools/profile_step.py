@@ -45,6 +45,32 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     step(); torch.cuda.synchronize()
 table(prof, "gpurun_out/kernels_train.txt")
 
+# the graph-replayed step: busy time vs span (launch gaps that remain inside the graph)
+def gaps(prof, tag):
+    evs = sorted(((e.time_range.start, e.time_range.end) for e in prof.events() if e.device_time_total > 0 and e.time_range.end > e.time_range.start))
+    if not evs:
+        return
+    span = evs[-1][1] - evs[0][0]
+    busy, cur_end, idle_small, idle_big, n_big = 0.0, evs[0][0], 0.0, 0.0, 0
+    for a, b in evs:
+        if a > cur_end:
+            g = a - cur_end
+            if g > 5: idle_big += g; n_big += 1
+            else: idle_small += g
+        busy += max(0.0, b - max(a, cur_end)); cur_end = max(cur_end, b)
+    print(f"{tag}: span {span/1e3:.2f} ms, busy {busy/1e3:.2f} ms, idle in gaps<=5us {idle_small/1e3:.2f} ms, idle in {n_big} gaps>5us {idle_big/1e3:.2f} ms, {len(evs)} device activities")
+gaps(prof, "eager step")
+gstep = T.GraphedTrainStep(model, opt, (x, y))
+print("graph captured:", gstep.graph is not None, gstep.error, "launches/step", gstep.launches_per_step)
+for _ in range(3): gstep((x, y))
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(10): gstep((x, y))
+torch.cuda.synchronize(); print(f"graphed step: {(time.perf_counter()-t0)*100:.2f} ms/step wall")
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    gstep((x, y)); torch.cuda.synchronize()
+gaps(prof, "graphed step")
+
 # sampling: one network evaluation, eval mode, batch 128, class conditional
 sm = build_edm(CIFAR10, num_classes=10, dropout_rate=0.0).to(dev).eval()
 with torch.no_grad():
