@@ -123,6 +123,10 @@ int tedm_scalelong_forward(const float* mean, const float* w1, const float* w2, 
                            float* gain, int B, int C, int R, tedm_stream_t stream);
 int tedm_scalelong_backward(const float* d_gain, const float* gain, const float* h_pre, const float* w1, const float* w2,
                             float* d_pre2, float* d_hpre, float* d_mean, int B, int C, int R, tedm_stream_t stream);
+/* dL/dw_hat of both ScaleLong layers, ACCUMULATED into dw2 [C][R] and dw1 [R][C+1] (zero them first):
+ * dw2 += d_pre2^T h,  dw1 += d_hpre^T aug  (autograd of networks.py:112-115) */
+int tedm_scalelong_wgrad(const float* d_pre2, const float* h, const float* d_hpre, const float* aug, float* dw2, float* dw1,
+                         int B, int C, int R, tedm_stream_t stream);
 /* UncertaintyNet (networks.py:91-103) */
 int tedm_uncertainty_forward(const float* fourier, const float* w1, const float* w2, const float* gain, float* aug,
                              float* h_pre, float* h, float* u_raw, float* u, int B, int F, tedm_stream_t stream);

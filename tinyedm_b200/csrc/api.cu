@@ -133,6 +133,10 @@ int tedm_scalelong_backward(const float* d_gain, const float* gain, const float*
   ScaleLongBwdArgs a{d_gain, gain, h_pre, w1, w2, d_pre2, d_hpre, d_mean, B, C, R};
   return scalelong_backward(a, ST(stream));
 }
+int tedm_scalelong_wgrad(const float* d_pre2, const float* h, const float* d_hpre, const float* aug, float* dw2, float* dw1,
+                         int B, int C, int R, tedm_stream_t stream) {
+  return scalelong_wgrad(d_pre2, h, d_hpre, aug, dw2, dw1, B, C, R, ST(stream));
+}
 int tedm_uncertainty_forward(const float* fourier, const float* w1, const float* w2, const float* gain, float* aug,
                              float* h_pre, float* h, float* u_raw, float* u, int B, int F, tedm_stream_t stream) {
   UncertaintyArgs a{fourier, w1, w2, gain, aug, h_pre, h, u_raw, u, B, F};

@@ -4,20 +4,21 @@
 // F.scaled_dot_product_attention(q, k, v) with scale 1/sqrt(hd) (:201), output channel = head*hd + d (:202).
 // qkv is (B,S,3C) bf16 with channel = {q,k,v}*C + head*hd + d (the weight bank permutes the qkv conv's rows).
 //
-// One CTA owns a SLAB of 256 query rows:
-//     S = 256 : one (image, head): 2 M-tiles of 128 queries, both attend to the same 256 keys;
-//     S =  64 : four consecutive (image, head) pairs: 2 M-tiles of 2 pairs each, each tile has its own 128 keys and a
-//               block-diagonal mask (a query only sees the 64 keys of its own pair).
-// Pipeline per CTA (9 warps):
-//     warp 8      TMA: Q, K, V slabs (3 x 32 KB, 128B-swizzled rows of 64 bf16)                      -> bar_load
-//     warps 0..7  pixel_norm of the 768 rows in shared memory (one row per thread and tensor)         -> fence, sync
-//     warp 8      tcgen05.mma  S_t = Q_t K_t^T   (M=128, N=keys, K=64)  fp32 in TMEM                  -> bar_s[t]
-//     warps 4t..  softmax of tile t straight out of TMEM (thread = query row): max, exp2, sum;
-//                 unnormalised P (bf16) -> swizzled shared memory (the A operand of the next MMA)     -> p_ready[t]
-//     warp 8      tcgen05.mma  O_t = P_t V_t     (M=128, N=64, K=keys; V is the MN-major B operand),
-//                 accumulating into the TMEM columns S_t no longer needs                              -> bar_o[t]
-//     warps 4t..  O / rowsum -> bf16 -> y, log-sum-exp -> lse
-// The S x S score matrix exists only in TMEM (512 columns = 2 tiles x 256 keys) and, as bf16 P, in shared memory.
+// One CTA owns ONE M-tile of 128 query rows; two CTAs are resident per SM (112 KB of shared memory, 256 TMEM columns
+// each) so that the TMA load / normalisation of one overlaps the MMA / softmax of the other:
+//     S = 256 : half of one (image, head): 128 queries, 256 keys;
+//     S =  64 : two consecutive (image, head) pairs: 128 queries, 128 keys and a block-diagonal mask (a query only sees
+//               the 64 keys of its own pair).
+// Pipeline per CTA (5 warps):
+//     warp 4      TMA: Q tile, K, V (rows of 64 bf16, 128B-swizzled)                                 -> bar_load
+//     warps 0..3  pixel_norm of every row in shared memory (thread-per-row)                           -> fence, sync
+//     warp 4      tcgen05.mma  S = Q K^T   (M=128, N=keys, K=64)  fp32 in TMEM                        -> bar_s
+//     warps 0..3  softmax straight out of TMEM (thread = query row): max, then per 64-key chunk exp2 / sum and the
+//                 unnormalised P chunk (bf16) -> a 2-slot ring in swizzled shared memory              -> p_ready[slot]
+//     warp 4      tcgen05.mma  O += P_c V_c (M=128, N=64, K=64; V is the MN-major B operand) into the TMEM columns
+//                 the softmax has already consumed; commit frees the ring slot                        -> p_free[slot], bar_o
+//     warps 0..3  O / rowsum -> bf16 -> y, log-sum-exp -> lse
+// The S x S score matrix exists only in TMEM and, 64 keys at a time as bf16 P, in shared memory.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -26,17 +27,18 @@ namespace tedm {
 namespace {
 
 constexpr int kHD = 64;
-constexpr int kSlabRows = 256;
-constexpr int kSlabBytes = kSlabRows * 128;                 // 32 KB: 256 rows of 64 bf16
+constexpr int kTileQ = 128;
+constexpr int kQBytes = kTileQ * 128;                       // 16 KB
+constexpr int kKVBytesMax = 256 * 128;                      // 32 KB each
 constexpr int kPChunkBytes = 128 * 128;                     // [128 queries][64 keys] bf16
-constexpr int kOffQ = 0, kOffK = kSlabBytes, kOffV = 2 * kSlabBytes, kOffP = 3 * kSlabBytes;
-constexpr int kOffBarsA = kOffP + 2 * 4 * kPChunkBytes;     // two tiles x up to 4 key chunks
-constexpr int kSmemBytesA = kOffBarsA + 128 + 1024;
-constexpr int kThreadsA = 288;
+constexpr int kOffQ = 0, kOffK = kQBytes, kOffV = kQBytes + kKVBytesMax, kOffP = kQBytes + 2 * kKVBytesMax;
+constexpr int kOffBarsA = kOffP + 2 * kPChunkBytes;
+constexpr int kSmemBytesA = kOffBarsA + 128;                // 114 816 B: two CTAs per SM
+constexpr int kThreadsA = 160;
 constexpr float kEpsA = 1e-4f;
 constexpr float kLog2eA = 1.4426950408889634f;
 constexpr float kLn2A = 0.6931471805599453f;
-static_assert(kSmemBytesA <= 232448, "shared memory budget");
+static_assert(2 * (kSmemBytesA + 1024) <= 233472, "two CTAs per SM");
 
 __device__ __forceinline__ uint4* prow(uint8_t* buf, int m, int j) {
   return reinterpret_cast<uint4*>(buf + m * 128 + ((j ^ (m & 7)) << 4));
@@ -63,39 +65,45 @@ __device__ __forceinline__ void normalize_row(uint8_t* slab, int r) {
   }
 }
 
-// NK = keys per M-tile (256 for S = 256, 128 for S = 64), PAIR = rows per (image, head) pair (= S)
+// NK = keys of the tile (256 for S = 256, 128 for S = 64)
 template <int S>
-__global__ void __launch_bounds__(kThreadsA, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ y, float* __restrict__ lse,
-                   int n_pairs, int heads, float scale) {
+__global__ void __launch_bounds__(kThreadsA, 2)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                   __nv_bfloat16* __restrict__ y, float* __restrict__ lse, int n_pairs, int heads, float scale) {
   constexpr int NK = S == 256 ? 256 : 128;
-  constexpr int PAIRS = kSlabRows / S;              // (image, head) pairs per CTA
-  constexpr int NCH = NK / 64;                      // 64-key chunks of P per tile
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int NCH = NK / 64;                      // 64-key chunks
+  constexpr int TILES_PER_PAIR = S == 256 ? 2 : 1;  // S = 64: one tile holds 2 pairs
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBarsA);
   uint64_t* bar_load = bars;          // TMA bytes
-  uint64_t* bar_s = bars + 1;         // [2] scores of tile t in TMEM
-  uint64_t* p_ready = bars + 3;       // [2] 128 softmax threads of tile t wrote P (and are done with S_t)
-  uint64_t* bar_o = bars + 5;         // [2] O_t in TMEM
+  uint64_t* bar_s = bars + 1;         // scores in TMEM
+  uint64_t* p_ready = bars + 2;       // [2] 128 softmax threads wrote ring slot (and are done with those S columns)
+  uint64_t* p_free = bars + 4;        // [2] the MMAs reading ring slot have completed
+  uint64_t* bar_o = bars + 6;         // O in TMEM
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = heads * kHD;
-  const int pair0 = blockIdx.x * PAIRS;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();      // the swizzled tiles need a 1024-byte aligned base
+  // tile -> (first pair, query offset)
+  const int tile = blockIdx.x;
+  const int pair0 = S == 256 ? tile / TILES_PER_PAIR : tile * 2;
+  const int q_off = S == 256 ? (tile % TILES_PER_PAIR) * kTileQ : 0;
 
-  if (warp == 8) {
+  if (warp == 4) {
     if (lane == 0) {
-      tma_prefetch_desc(&tmap_qkv);
+      tma_prefetch_desc(&tmap_q);
+      tma_prefetch_desc(&tmap_kv);
       mbar_init(bar_load, 1);
-      for (int t = 0; t < 2; ++t) {
-        mbar_init(&bar_s[t], 1);
-        mbar_init(&p_ready[t], 128);
-        mbar_init(&bar_o[t], 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_o, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&p_ready[i], 128);
+        mbar_init(&p_free[i], 1);
       }
       mbar_fence_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_ptr, 512);
+    tmem_alloc(tmem_ptr, 256);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -103,128 +111,129 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 8) {
+  if (warp == 4) {
     if (lane == 0) {
-      // ---- loads: per pair, S rows x 64 channels of q, k and v (rows of image b, channel block of the head) ----
-      mbar_expect_tx(bar_load, 3 * kSlabBytes);
-      for (int pp = 0; pp < PAIRS; ++pp) {
-        int pair = pair0 + pp;
-        if (pair >= n_pairs) pair = n_pairs - 1;          // tail CTA: duplicate the last pair (results discarded)
-        const int b = pair / heads, head = pair - b * heads;
-        const int row = b * S;
-        for (int part = 0; part < 3; ++part)
-          tma_load_2d(smem + part * kSlabBytes + pp * S * 128, &tmap_qkv, bar_load, part * C + head * kHD, row);
+      mbar_expect_tx(bar_load, kQBytes + 2 * NK * 128);
+      if (S == 256) {
+        const int b = pair0 / heads, head = pair0 - b * heads;
+        tma_load_2d(smem + kOffQ, &tmap_q, bar_load, head * kHD, b * S + q_off);
+        tma_load_2d(smem + kOffK, &tmap_kv, bar_load, C + head * kHD, b * S);
+        tma_load_2d(smem + kOffV, &tmap_kv, bar_load, 2 * C + head * kHD, b * S);
+      } else {
+        for (int pp = 0; pp < 2; ++pp) {
+          int pair = pair0 + pp;
+          if (pair >= n_pairs) pair = n_pairs - 1;      // tail tile: duplicate the last pair (results discarded)
+          const int b = pair / heads, head = pair - b * heads;
+          tma_load_2d(smem + kOffQ + pp * 64 * 128, &tmap_kv, bar_load, head * kHD, b * S);
+          tma_load_2d(smem + kOffK + pp * 64 * 128, &tmap_kv, bar_load, C + head * kHD, b * S);
+          tma_load_2d(smem + kOffV + pp * 64 * 128, &tmap_kv, bar_load, 2 * C + head * kHD, b * S);
+        }
       }
     }
   } else {
-    // ---- pixel_norm of q, k, v rows (thread i: row i of each slab) ----
+    // ---- pixel_norm of the q, k, v rows (thread-per-row) ----
     mbar_wait_bounded(bar_load, 0);
-    const int r = threadIdx.x;
-    normalize_row(smem + kOffQ, r);
-    normalize_row(smem + kOffK, r);
-    normalize_row(smem + kOffV, r);
+    normalize_row(smem + kOffQ, threadIdx.x);
+    for (int r = threadIdx.x; r < NK; r += 128) {
+      normalize_row(smem + kOffK, r);
+      normalize_row(smem + kOffV, r);
+    }
     fence_proxy_async_smem();
   }
   __syncthreads();
 
-  if (warp == 8) {
+  if (warp == 4) {
     if (lane == 0) {
       tc_fence_after();
-      // ---- S_t = Q_t K_t^T ----
-      const uint32_t idesc_s = make_idesc_bf16(128, NK, 0, 0);
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const uint32_t q_addr = smem_u32(smem + kOffQ + t * 128 * 128);
-        const uint32_t k_addr = smem_u32(smem + kOffK + (S == 256 ? 0 : t * 128 * 128));
-        const uint64_t a_desc = make_smem_desc_sw128(q_addr, 0, 1024);
-        const uint64_t b_desc = make_smem_desc_sw128(k_addr, 0, 1024);
+      {  // ---- S = Q K^T ----
+        const uint32_t idesc_s = make_idesc_bf16(128, NK, 0, 0);
+        const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem + kOffQ), 0, 1024);
+        const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem + kOffK), 0, 1024);
 #pragma unroll
         for (int k = 0; k < kHD / 16; ++k)
-          umma_bf16(tmem_base + t * 256, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(&bar_s[t]);
+          umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(bar_s);
       }
-      // ---- O_t = P_t V_t ----
+      // ---- O += P_c V_c, chunk by chunk through the 2-slot ring ----
       const uint32_t idesc_o = make_idesc_bf16(128, kHD, 0, 1);
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        mbar_wait_bounded(&p_ready[t], 0);
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c) {
+        const int slot = c & 1;
+        mbar_wait_bounded(&p_ready[slot], (c >> 1) & 1);
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(smem + kOffV + (S == 256 ? 0 : t * 128 * 128));
+        const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem + kOffP + slot * kPChunkBytes), 0, 1024);
+        // V rows (keys) 64c .. 64c+63: MN-major B operand, 16 keys (K) = 16 rows of 128 B per MMA
+        const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem + kOffV + c * 64 * 128), 64 * 128, 1024);
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const uint32_t p_addr = smem_u32(smem + kOffP + (t * 4 + c) * kPChunkBytes);
-          const uint64_t a_desc = make_smem_desc_sw128(p_addr, 0, 1024);
-          // V rows (keys) 64c .. 64c+63: MN-major B operand, 16 keys (K) = 16 rows of 128 B per MMA
-          const uint64_t b_desc = make_smem_desc_sw128(v_addr + c * 64 * 128, 64 * 128, 1024);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + t * 256, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 128), idesc_o,
-                      (c | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(&bar_o[t]);
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 128), idesc_o, (c | k) != 0 ? 1u : 0u);
+        umma_commit(&p_free[slot]);
       }
+      umma_commit(bar_o);
     }
   } else {
-    // ---- softmax + output of tile t (warps 4t .. 4t+3; thread = query row) ----
-    const int t = warp >> 2, q = warp & 3;
-    const int m = q * 32 + lane;                       // row within the tile
-    const int slab_row = t * 128 + m;
-    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + t * 256;
+    // ---- softmax + output (thread = query row) ----
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
     // keys this row may see: all NK for S = 256; the 64 of its own pair for S = 64
     const int kb = S == 256 ? 0 : (m >> 6) * 64;
     const int kn = S == 256 ? NK : 64;
     const float sc = scale * kLog2eA;
-    mbar_wait_bounded(&bar_s[t], 0);
+    mbar_wait_bounded(bar_s, 0);
     tc_fence_after();
-    float mx = -INFINITY;
+    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // 4 independent chains (a single one is latency bound)
 #pragma unroll 1
     for (int c0 = 0; c0 < kn; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(t_row + kb + c0, r);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+      for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(r[i]));
     }
+    const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
     const float mxs = mx * sc;
-    float sum = 0.f;
-    uint8_t* pbuf = smem + kOffP + t * 4 * kPChunkBytes;
+    float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-    for (int c0 = 0; c0 < NK; c0 += 32) {
-      uint4* dst[4];
+    for (int c = 0; c < NCH; ++c) {
+      const int slot = c & 1;
+      uint8_t* pbuf = smem + kOffP + slot * kPChunkBytes;
+      if (c >= 2) mbar_wait_bounded(&p_free[slot], ((c >> 1) - 1) & 1);   // the MMAs of chunk c-2 released the slot
+      const bool live = (c * 64 >= kb) && (c * 64 < kb + kn);
 #pragma unroll
-      for (int g = 0; g < 4; ++g) dst[g] = prow(pbuf + (c0 >> 6) * kPChunkBytes, m, ((c0 & 63) >> 3) + g);
-      if (c0 >= kb && c0 < kb + kn) {
-        uint32_t r[32];
-        tmem_ld32(t_row + c0, r);
-        tmem_ld_wait();
-        float pv[32];
+      for (int h = 0; h < 2; ++h) {
+        if (live) {
+          uint32_t r[32];
+          tmem_ld32(t_row + c * 64 + h * 32, r);
+          tmem_ld_wait();
+          float pv[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          pv[i] = exp2f(fmaf(__uint_as_float(r[i]), sc, -mxs));
-          // the MMA consumes bf16 probabilities: the row sum uses the same rounded values (as SDPA's bf16 P does)
-          pv[i] = bf16_round(pv[i]);
-          sum += pv[i];
+          for (int i = 0; i < 32; ++i) {
+            pv[i] = exp2f(fmaf(__uint_as_float(r[i]), sc, -mxs));
+            sum4[i & 3] += pv[i];     // fp32 row sum of the unrounded probabilities (as the warp-MMA kernel does)
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 o;
+            o.x = pack_bf16(pv[g * 8 + 0], pv[g * 8 + 1]); o.y = pack_bf16(pv[g * 8 + 2], pv[g * 8 + 3]);
+            o.z = pack_bf16(pv[g * 8 + 4], pv[g * 8 + 5]); o.w = pack_bf16(pv[g * 8 + 6], pv[g * 8 + 7]);
+            *prow(pbuf, m, h * 4 + g) = o;
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) *prow(pbuf, m, h * 4 + g) = make_uint4(0, 0, 0, 0);   // keys of the other pair
         }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 o;
-          o.x = pack_bf16(pv[g * 8 + 0], pv[g * 8 + 1]); o.y = pack_bf16(pv[g * 8 + 2], pv[g * 8 + 3]);
-          o.z = pack_bf16(pv[g * 8 + 4], pv[g * 8 + 5]); o.w = pack_bf16(pv[g * 8 + 6], pv[g * 8 + 7]);
-          *dst[g] = o;
-        }
-      } else {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) *dst[g] = make_uint4(0, 0, 0, 0);   // masked keys of the other pair
       }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&p_ready[slot]);
     }
-    tc_fence_before();
-    fence_proxy_async_smem();
-    mbar_arrive(&p_ready[t]);
     // ---- epilogue ----
-    mbar_wait_bounded(&bar_o[t], 0);
+    mbar_wait_bounded(bar_o, 0);
     tc_fence_after();
-    const int pair = pair0 + slab_row / S;
-    const int s_idx = slab_row % S;
+    const int pair = S == 256 ? pair0 : pair0 + (m >> 6);
+    const int s_idx = S == 256 ? q_off + m : (m & 63);
+    const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
     const float inv = 1.0f / sum;
     uint32_t o0[32], o1[32];
     tmem_ld32(t_row, o0);
@@ -257,29 +266,30 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 4) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, 256);
   }
 }
 
 template <int S>
 int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* y, float* lse, int B, int heads, cudaStream_t stream) {
   const int C = heads * kHD;
-  CUtensorMap tm;
+  CUtensorMap tq, tkv;
   uint64_t dims[2] = {(uint64_t)3 * C, (uint64_t)B * S};
   uint64_t strides[1] = {(uint64_t)3 * C * 2};
-  uint32_t box[2] = {64, (uint32_t)S};
-  if (encode_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) != 0) return -1;
+  uint32_t box_q[2] = {64, (uint32_t)(S == 256 ? kTileQ : 64)};   // 128 queries of a head (S = 256) / one pair (S = 64)
+  uint32_t box_kv[2] = {64, (uint32_t)S};                          // all keys of a head
+  if (encode_tmap(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, box_q, CU_TENSOR_MAP_SWIZZLE_128B) != 0) return -1;
+  if (encode_tmap(&tkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, box_kv, CU_TENSOR_MAP_SWIZZLE_128B) != 0) return -1;
   static bool configured = false;
   if (!configured) {
     TEDM_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesA));
     configured = true;
   }
   const int n_pairs = B * heads;
-  const int per_cta = kSlabRows / S;
-  const int grid = (n_pairs + per_cta - 1) / per_cta;
-  attn_fwd_tc_kernel<S><<<grid, kThreadsA, kSmemBytesA, stream>>>(tm, y, lse, n_pairs, heads, 1.0f / sqrtf((float)kHD));
+  const int grid = S == 256 ? n_pairs * 2 : (n_pairs + 1) / 2;
+  attn_fwd_tc_kernel<S><<<grid, kThreadsA, kSmemBytesA, stream>>>(tq, tkv, y, lse, n_pairs, heads, 1.0f / sqrtf((float)kHD));
   TEDM_LAUNCH_CHECK();
   return 0;
 }

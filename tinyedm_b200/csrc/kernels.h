@@ -192,6 +192,8 @@ struct ScaleLongBwdArgs {
   int B, C, R;
 };
 int scalelong_backward(const ScaleLongBwdArgs& a, cudaStream_t stream);
+int scalelong_wgrad(const float* d_pre2, const float* h, const float* d_hpre, const float* aug, float* dw2, float* dw1, int B,
+                    int C, int R, cudaStream_t stream);
 
 struct UncertaintyArgs {
   const float* fourier; const float* w1; const float* w2; const float* gain;

@@ -244,6 +244,31 @@ scalelong_bwd_kernel(const ScaleLongBwdArgs a) {
   }
 }
 
+// Weight gradients of both ScaleLong layers in ONE launch (they were two split-K sgemm launches + two memsets per skip
+// block): dW2[c][j] += sum_b d_pre2[b][c] h[b][j]  (C x R),  dW1[j][c] += sum_b d_hpre[b][j] aug[b][c]  (R x (C+1)).
+// One thread per output element, blockIdx.y splits the batch; results are accumulated atomically (dw zeroed by the caller).
+__global__ void __launch_bounds__(256)
+scalelong_wgrad_kernel(const float* __restrict__ d_pre2, const float* __restrict__ h, const float* __restrict__ d_hpre,
+                       const float* __restrict__ aug, float* __restrict__ dw2, float* __restrict__ dw1, int B, int C, int R) {
+  const int n2 = C * R, n1 = R * (C + 1);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n1 + n2) return;
+  const int chunk = (B + gridDim.y - 1) / gridDim.y;
+  const int b0 = blockIdx.y * chunk;
+  const int b1 = b0 + chunk < B ? b0 + chunk : B;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (i < n2) {
+    const int c = i / R, j = i - c * R;
+    for (int b = b0; b < b1; ++b) acc[b & 3] += d_pre2[(size_t)b * C + c] * h[(size_t)b * R + j];
+    atomicAdd(dw2 + i, (acc[0] + acc[1]) + (acc[2] + acc[3]));
+  } else {
+    const int k = i - n2;
+    const int j = k / (C + 1), c = k - j * (C + 1);
+    for (int b = b0; b < b1; ++b) acc[b & 3] += d_hpre[(size_t)b * R + j] * aug[(size_t)b * (C + 1) + c];
+    atomicAdd(dw1 + k, (acc[0] + acc[1]) + (acc[2] + acc[3]));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // UncertaintyNet (per batch row); in = hidden = F
 // ------------------------------------------------------------------------------------------------
@@ -631,6 +656,15 @@ int scalelong_forward(const ScaleLongArgs& a, cudaStream_t stream) {
 }
 int scalelong_backward(const ScaleLongBwdArgs& a, cudaStream_t stream) {
   scalelong_bwd_kernel<<<a.B, 256, (a.C + a.R) * sizeof(float), stream>>>(a);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+int scalelong_wgrad(const float* d_pre2, const float* h, const float* d_hpre, const float* aug, float* dw2, float* dw1, int B,
+                    int C, int R, cudaStream_t stream) {
+  if (B <= 0) return 0;
+  const int n = C * R + R * (C + 1);
+  dim3 grid((n + 255) / 256, B >= 64 ? 8 : 1);
+  scalelong_wgrad_kernel<<<grid, 256, 0, stream>>>(d_pre2, h, d_hpre, aug, dw2, dw1, B, C, R);
   TEDM_LAUNCH_CHECK();
   return 0;
 }

@@ -142,32 +142,60 @@ weight_prep_fwd_kernel(const WeightDesc* __restrict__ table, int n_tensors, int 
       const int row = src_row(d, o0 + r);
       float* w = wbase + (size_t)row * fan_in + (size_t)c0 * taps;
       const float s1 = s_s1[r], inv_s = s_inv[r];
-      for (int j = lane; j < nel; j += 32) {
-        const float v = w[j] * s1;
-        if (training) w[j] = v;
-        const float wh = v * inv_s;
-        if (out_f32 != nullptr) out_f32[(size_t)row * fan_in + (size_t)c0 * taps + j] = wh;
-        tile[r * kTileStride + j] = wh;
+      if ((nel & 3) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 && out_f32 == nullptr) {
+        float4* w4 = reinterpret_cast<float4*>(w);
+        for (int j4 = lane; j4 < nel / 4; j4 += 32) {
+          float4 v = w4[j4];
+          v.x *= s1; v.y *= s1; v.z *= s1; v.w *= s1;
+          if (training) w4[j4] = v;
+          float* t = tile + r * kTileStride + 4 * j4;
+          t[0] = v.x * inv_s; t[1] = v.y * inv_s; t[2] = v.z * inv_s; t[3] = v.w * inv_s;
+        }
+      } else {
+        for (int j = lane; j < nel; j += 32) {
+          const float v = w[j] * s1;
+          if (training) w[j] = v;
+          const float wh = v * inv_s;
+          if (out_f32 != nullptr) out_f32[(size_t)row * fan_in + (size_t)c0 * taps + j] = wh;
+          tile[r * kTileStride + j] = wh;
+        }
       }
     }
     __syncthreads();
     if (out_fwd != nullptr) {
-      // (r, tap, ci): ci fastest -> 2-byte writes of consecutive threads are contiguous
-      const int per_row = taps * nci;
-      for (int idx = threadIdx.x; idx < nrows * per_row; idx += kFwdThreads) {
-        const int r = idx / per_row, rem = idx - r * per_row;
-        const int tap = rem / nci, cl = rem - tap * nci;
-        out_fwd[(size_t)(o0 + r) * d.kpad + tap * cin + c0 + cl] = __float2bfloat16_rn(tile[r * kTileStride + cl * taps + tap]);
+      // one warp per (row, tap): lanes run along ci, two channels per lane (4-byte stores, 128 contiguous bytes per warp);
+      // nested loops instead of per-element div/mod (the element-indexed version was integer-instruction bound)
+      for (int rt = warp; rt < nrows * taps; rt += kFwdThreads / 32) {
+        const int r = rt / taps, tap = rt - r * taps;
+        const float* trow = tile + r * kTileStride + tap;
+        __nv_bfloat16* orow_p = out_fwd + (size_t)(o0 + r) * d.kpad + tap * cin + c0;
+        if ((nci & 1) == 0 && ((reinterpret_cast<uintptr_t>(orow_p) & 3) == 0)) {
+          for (int cl = 2 * lane; cl < nci; cl += 64)
+            *reinterpret_cast<uint32_t*>(orow_p + cl) = pack_bf16(trow[cl * taps], trow[(cl + 1) * taps]);
+        } else {
+          for (int cl = lane; cl < nci; cl += 32) orow_p[cl] = __float2bfloat16_rn(trow[cl * taps]);
+        }
       }
     }
     if (out_dgrad != nullptr) {
-      // (ci, tap, r): r fastest -> the 16 rows of a (ci, tap) pair form one 32-byte sector
-      for (int idx = threadIdx.x; idx < nel * kGroupRows; idx += kFwdThreads) {
-        const int r = idx & (kGroupRows - 1), j = idx >> 4;
-        if (r < nrows) {
+      // (ci, tap) pairs x 16 rows: 8 lanes cover the 16 rows of a pair with 4-byte stores (one 32-byte sector), so a
+      // warp handles 4 pairs per pass; pairs are walked as j = cl * taps + tap without div/mod in the inner loop
+      const int rp = (lane & 7) * 2;           // this lane's two rows
+      const int sub = lane >> 3;               // which of the warp's 4 pairs
+      if (nrows == kGroupRows && (d.rows & 1) == 0) {
+        for (int j = warp * 4 + sub; j < nel; j += (kFwdThreads / 32) * 4) {
           const int cl = j / taps, tap = j - cl * taps;
-          out_dgrad[((size_t)(c0 + cl) * taps + (taps - 1 - tap)) * d.rows + o0 + r] =
-              __float2bfloat16_rn(tile[r * kTileStride + j]);
+          const uint32_t v = pack_bf16(tile[rp * kTileStride + j], tile[(rp + 1) * kTileStride + j]);
+          *reinterpret_cast<uint32_t*>(out_dgrad + ((size_t)(c0 + cl) * taps + (taps - 1 - tap)) * d.rows + o0 + rp) = v;
+        }
+      } else {
+        for (int idx = threadIdx.x; idx < nel * kGroupRows; idx += kFwdThreads) {
+          const int r = idx & (kGroupRows - 1), j = idx >> 4;
+          if (r < nrows) {
+            const int cl = j / taps, tap = j - cl * taps;
+            out_dgrad[((size_t)(c0 + cl) * taps + (taps - 1 - tap)) * d.rows + o0 + r] =
+                __float2bfloat16_rn(tile[r * kTileStride + j]);
+          }
         }
       }
     }

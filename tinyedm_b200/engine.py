@@ -641,9 +641,7 @@ class DenoiserEngine:
         ops.channel_dot(g_cat, S["skip"], d_gain, Cs, bp.cin, 1.0)
         s1, s2 = bp.w["sl1"], bp.w["sl2"]
         d_pre2, d_hpre, d_mean = ops.scalelong_backward(d_gain, S["gain"], S["h_pre"], s1.f32, s2.f32)
-        R = s1.rows
-        ops.sgemm(d_pre2, S["hh"], s2.ghat, Cs, R, B, Cs, R, R, True, False)
-        ops.sgemm(d_hpre, S["aug"], s1.ghat, R, Cs + 1, B, R, Cs + 1, Cs + 1, True, False)
+        ops.scalelong_wgrad(d_pre2, S["hh"], d_hpre, S["aug"], s2.ghat, s1.ghat)   # into the zeroed g_hat buffer
         g_in, acc = self._take_g_in(bp, pending, (B, Hin, Win, bp.cin), dev)
         g_skip = torch.empty((B, Hin, Win, Cs), device=dev, dtype=BF16)
         ops.block_prep_backward(g_res=g_cat, beta=1.0, g_a=None, x=None, nrm=None, gain=S["gain"], d_mean=d_mean,

@@ -241,6 +241,14 @@ def scalelong_backward(d_gain: Tensor, gain: Tensor, h_pre: Tensor, w1: Tensor, 
     return d_pre2, d_hpre, d_mean
 
 
+def scalelong_wgrad(d_pre2: Tensor, h: Tensor, d_hpre: Tensor, aug: Tensor, dw2: Tensor, dw1: Tensor) -> None:
+    """dw2[C][R] += d_pre2^T h ; dw1[R][C+1] += d_hpre^T aug (both accumulated: zero them first)."""
+    B, C = d_pre2.shape
+    R = h.shape[1]
+    _lib.call("tedm_scalelong_wgrad", d_pre2.data_ptr(), h.data_ptr(), d_hpre.data_ptr(), aug.data_ptr(), dw2.data_ptr(),
+              dw1.data_ptr(), B, C, R, _stream())
+
+
 def uncertainty_forward(fourier: Tensor, w1: Tensor, w2: Tensor, gain: Tensor):
     B, F_ = fourier.shape
     dev = fourier.device
