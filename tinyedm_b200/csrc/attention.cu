@@ -589,6 +589,11 @@ int attention_forward(const __nv_bfloat16* qkv, __nv_bfloat16* y, float* lse, in
 int attention_backward(const __nv_bfloat16* qkv, const __nv_bfloat16* y, const __nv_bfloat16* g_y, const float* lse,
                        float* delta, __nv_bfloat16* g_qkv, int B, int S, int heads, int hd, cudaStream_t stream) {
   if (check_dims(S, hd, heads) != 0) return -1;
+  static const bool use_tc = [] { const char* e = getenv("TEDM_ATTN_TC"); return !(e != nullptr && e[0] == '0'); }();
+  // tcgen05 backward: measured 296 us vs 325 us at S = 256 (B = 256), but 62 us vs 45 us at S = 64 (one CTA per SM, phases
+  // not overlapped): the small problem stays on the warp-MMA kernels
+  if (use_tc && attention_tc_supported(S, hd) && S == 256)
+    return attention_backward_tc(qkv, y, g_y, lse, delta, g_qkv, B, S, heads, stream);
   switch (hd) {
     case 32: return launch_bwd<32, 64>(qkv, y, g_y, lse, delta, g_qkv, B, S, heads, stream);
     case 64: return launch_bwd<64, 64>(qkv, y, g_y, lse, delta, g_qkv, B, S, heads, stream);

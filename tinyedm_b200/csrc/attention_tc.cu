@@ -272,6 +272,521 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   }
 }
 
+// =====================================================================================================================
+// Backward (autograd of networks.py:195-201). Same tiling as the forward, two kernels without atomics:
+//   dq  kernel: tile = 128 queries;  S = Qn Kn^T and dP = dO Vn^T into TMEM (2 x 256 columns), per 64-key chunk
+//               dS = exp2(S c - lse) (dP - delta) / sqrt(hd) -> bf16 ring -> dQn += dS Kn; also writes delta = rowsum(dO o O)
+//   dkv kernel: tile = 128 keys;     S^T = Kn Qn^T and dP^T = Vn dO^T into TMEM, per 64-query chunk P^T and dS^T -> two
+//               bf16 rings -> dVn += P^T dO, dKn += dS^T Qn
+// Each result row then goes through the adjoint of its pixel norm  g_u = g/n - y (g.y) / ((n - eps) hd)  in registers.
+// =====================================================================================================================
+constexpr int kThreadsB = 160;
+// dq: Q tile 16K | dO tile 16K | K 32K | V 32K | dS ring 2 x 16K
+constexpr int kDqOffQ = 0, kDqOffDO = 16384, kDqOffK = 32768, kDqOffV = 65536, kDqOffRing = 98304, kDqOffBars = 131072;
+constexpr int kDqSmem = kDqOffBars + 128;
+// dkv: K tile 16K | V tile 16K | Q 32K | dO 32K | P^T ring 2 x 16K | dS^T ring 2 x 16K | lse2[256] | delta[256]
+constexpr int kKvOffK = 0, kKvOffV = 16384, kKvOffQ = 32768, kKvOffDO = 65536, kKvOffRingP = 98304, kKvOffRingS = 131072,
+              kKvOffVec = 163840, kKvOffBars = 163840 + 2048;
+constexpr int kKvSmem = kKvOffBars + 128;
+
+// pixel-norm adjoint of one 64-element gradient row held as two 32-float halves; y = the normalised row in a swizzled slab
+__device__ __forceinline__ void norm_adjoint_store(const uint32_t (&g0)[32], const uint32_t (&g1)[32], uint8_t* slab, int r,
+                                                   float n, __nv_bfloat16* dst) {
+  float yv[64];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint4 u = *prow(slab, r, j);
+    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+    yv[j * 8 + 0] = a.x; yv[j * 8 + 1] = a.y; yv[j * 8 + 2] = b.x; yv[j * 8 + 3] = b.y;
+    yv[j * 8 + 4] = c.x; yv[j * 8 + 5] = c.y; yv[j * 8 + 6] = d.x; yv[j * 8 + 7] = d.y;
+  }
+  float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    d4[i & 3] += __uint_as_float(g0[i]) * yv[i];
+    d4[i & 3] += __uint_as_float(g1[i]) * yv[32 + i];
+  }
+  const float dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+  const float inv_n = 1.0f / n;
+  const float k = dot / (fmaxf(n - kEpsA, 1e-20f) * kHD);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int i = j * 8 + e;
+      const float g = i < 32 ? __uint_as_float(g0[i]) : __uint_as_float(g1[i - 32]);
+      o[e] = g * inv_n - yv[i] * k;
+    }
+    uint4 u;
+    u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
+    reinterpret_cast<uint4*>(dst)[j] = u;
+  }
+}
+
+// like normalize_row, returns n = eps + rms of the raw row
+__device__ __forceinline__ float normalize_row_n(uint8_t* slab, int r) {
+  uint4 v[8];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v[j] = *prow(slab, r, j);
+    const float2 a = unpack_bf16(v[j].x), b = unpack_bf16(v[j].y), c = unpack_bf16(v[j].z), d = unpack_bf16(v[j].w);
+    ss += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
+  }
+  const float n = kEpsA + sqrtf(ss * (1.0f / kHD));
+  const float inv = 1.0f / n;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 a = unpack_bf16(v[j].x), b = unpack_bf16(v[j].y), c = unpack_bf16(v[j].z), d = unpack_bf16(v[j].w);
+    uint4 o;
+    o.x = pack_bf16(a.x * inv, a.y * inv); o.y = pack_bf16(b.x * inv, b.y * inv);
+    o.z = pack_bf16(c.x * inv, c.y * inv); o.w = pack_bf16(d.x * inv, d.y * inv);
+    *prow(slab, r, j) = o;
+  }
+  return n;
+}
+
+template <int S>
+__global__ void __launch_bounds__(kThreadsB, 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                      const __grid_constant__ CUtensorMap tmap_do, const __nv_bfloat16* __restrict__ y,
+                      const float* __restrict__ lse, float* __restrict__ delta, __nv_bfloat16* __restrict__ g_qkv,
+                      int n_pairs, int heads, float scale) {
+  constexpr int NK = S == 256 ? 256 : 128;
+  constexpr int NCH = NK / 64;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDqOffBars);
+  uint64_t* bar_load = bars;
+  uint64_t* bar_s = bars + 1;
+  uint64_t* p_ready = bars + 2;   // [2]
+  uint64_t* p_free = bars + 4;    // [2]
+  uint64_t* bar_o = bars + 6;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = heads * kHD;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  const int tile = blockIdx.x;
+  const int pair0 = S == 256 ? tile / 2 : tile * 2;
+  const int q_off = S == 256 ? (tile & 1) * kTileQ : 0;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_q);
+      tma_prefetch_desc(&tmap_kv);
+      tma_prefetch_desc(&tmap_do);
+      mbar_init(bar_load, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_o, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&p_ready[i], 128);
+        mbar_init(&p_free[i], 1);
+      }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  float n_q = 1.f, dl = 0.f, ls2 = 0.f;
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_load, 2 * kQBytes + 2 * NK * 128);
+      if (S == 256) {
+        const int b = pair0 / heads, head = pair0 - b * heads;
+        tma_load_2d(smem + kDqOffQ, &tmap_q, bar_load, head * kHD, b * S + q_off);
+        tma_load_2d(smem + kDqOffDO, &tmap_do, bar_load, head * kHD, b * S + q_off);
+        tma_load_2d(smem + kDqOffK, &tmap_kv, bar_load, C + head * kHD, b * S);
+        tma_load_2d(smem + kDqOffV, &tmap_kv, bar_load, 2 * C + head * kHD, b * S);
+      } else {
+        for (int pp = 0; pp < 2; ++pp) {
+          int pair = pair0 + pp;
+          if (pair >= n_pairs) pair = n_pairs - 1;
+          const int b = pair / heads, head = pair - b * heads;
+          tma_load_2d(smem + kDqOffQ + pp * 8192, &tmap_kv, bar_load, head * kHD, b * S);
+          tma_load_2d(smem + kDqOffDO + pp * 8192, &tmap_do, bar_load, head * kHD, b * S);
+          tma_load_2d(smem + kDqOffK + pp * 8192, &tmap_kv, bar_load, C + head * kHD, b * S);
+          tma_load_2d(smem + kDqOffV + pp * 8192, &tmap_kv, bar_load, 2 * C + head * kHD, b * S);
+        }
+      }
+    }
+  } else {
+    const int m = threadIdx.x;
+    const int pair = S == 256 ? pair0 : pair0 + (m >> 6);
+    const int s_idx = S == 256 ? q_off + m : (m & 63);
+    const bool live = pair < n_pairs;
+    const int pr = live ? pair : n_pairs - 1;
+    const int b = pr / heads, head = pr - b * heads;
+    // delta = sum_d dO * O of this thread's query row (O straight from global, dO from the TMA tile)
+    const uint4* orow = reinterpret_cast<const uint4*>(y + ((long long)b * S + s_idx) * C + head * kHD);
+    uint4 ov[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ov[j] = orow[j];
+    ls2 = lse[(long long)pr * S + s_idx] * kLog2eA;
+    mbar_wait_bounded(bar_load, 0);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint4 g = *prow(smem + kDqOffDO, m, j);
+      const float2 g0 = unpack_bf16(g.x), g1 = unpack_bf16(g.y), g2 = unpack_bf16(g.z), g3 = unpack_bf16(g.w);
+      const float2 o0 = unpack_bf16(ov[j].x), o1 = unpack_bf16(ov[j].y), o2 = unpack_bf16(ov[j].z), o3 = unpack_bf16(ov[j].w);
+      acc += g0.x * o0.x + g0.y * o0.y + g1.x * o1.x + g1.y * o1.y + g2.x * o2.x + g2.y * o2.y + g3.x * o3.x + g3.y * o3.y;
+    }
+    dl = acc;
+    if (live) delta[(long long)pair * S + s_idx] = acc;
+    n_q = normalize_row_n(smem + kDqOffQ, m);
+    for (int r = m; r < NK; r += 128) {
+      normalize_row(smem + kDqOffK, r);
+      normalize_row(smem + kDqOffV, r);
+    }
+    fence_proxy_async_smem();
+  }
+  __syncthreads();
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tc_fence_after();
+      const uint32_t idesc_s = make_idesc_bf16(128, NK, 0, 0);
+      {
+        const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem + kDqOffQ), 0, 1024);
+        const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem + kDqOffK), 0, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc_s, k != 0 ? 1u : 0u);
+      }
+      {
+        const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem + kDqOffDO), 0, 1024);
+        const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem + kDqOffV), 0, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + 256, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc_s, k != 0 ? 1u : 0u);
+      }
+      umma_commit(bar_s);
+      const uint32_t idesc_o = make_idesc_bf16(128, kHD, 0, 1);
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c) {
+        const int slot = c & 1;
+        mbar_wait_bounded(&p_ready[slot], (c >> 1) & 1);
+        tc_fence_after();
+        const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem + kDqOffRing + slot * kPChunkBytes), 0, 1024);
+        const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem + kDqOffK + c * 64 * 128), 64 * 128, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 128), idesc_o, (c | k) != 0 ? 1u : 0u);
+        umma_commit(&p_free[slot]);
+      }
+      umma_commit(bar_o);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int kb = S == 256 ? 0 : (m >> 6) * 64;
+    const int kn = S == 256 ? NK : 64;
+    const float sc = scale * kLog2eA;
+    mbar_wait_bounded(bar_s, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c) {
+      const int slot = c & 1;
+      uint8_t* pbuf = smem + kDqOffRing + slot * kPChunkBytes;
+      if (c >= 2) mbar_wait_bounded(&p_free[slot], ((c >> 1) - 1) & 1);
+      const bool on = (c * 64 >= kb) && (c * 64 < kb + kn);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (on) {
+          uint32_t rs[32], rp[32];
+          tmem_ld32(t_row + c * 64 + h * 32, rs);
+          tmem_ld32(t_row + 256 + c * 64 + h * 32, rp);
+          tmem_ld_wait();
+          float ds[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            ds[i] = exp2f(fmaf(__uint_as_float(rs[i]), sc, -ls2)) * (__uint_as_float(rp[i]) - dl) * scale;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 o;
+            o.x = pack_bf16(ds[g * 8 + 0], ds[g * 8 + 1]); o.y = pack_bf16(ds[g * 8 + 2], ds[g * 8 + 3]);
+            o.z = pack_bf16(ds[g * 8 + 4], ds[g * 8 + 5]); o.w = pack_bf16(ds[g * 8 + 6], ds[g * 8 + 7]);
+            *prow(pbuf, m, h * 4 + g) = o;
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) *prow(pbuf, m, h * 4 + g) = make_uint4(0, 0, 0, 0);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&p_ready[slot]);
+    }
+    mbar_wait_bounded(bar_o, 0);
+    tc_fence_after();
+    const int pair = S == 256 ? pair0 : pair0 + (m >> 6);
+    const int s_idx = S == 256 ? q_off + m : (m & 63);
+    uint32_t g0[32], g1[32];
+    tmem_ld32(t_row, g0);
+    tmem_ld32(t_row + 32, g1);
+    tmem_ld_wait();
+    if (pair < n_pairs) {
+      const int b = pair / heads, head = pair - b * heads;
+      norm_adjoint_store(g0, g1, smem + kDqOffQ, m, n_q, g_qkv + ((long long)b * S + s_idx) * 3 * C + head * kHD);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int S>
+__global__ void __launch_bounds__(kThreadsB, 1)
+attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_constant__ CUtensorMap tmap_all,
+                       const __grid_constant__ CUtensorMap tmap_do_all, const float* __restrict__ lse,
+                       const float* __restrict__ delta, __nv_bfloat16* __restrict__ g_qkv, int n_pairs, int heads,
+                       float scale) {
+  constexpr int NQ = S == 256 ? 256 : 128;   // queries seen by the tile's keys
+  constexpr int NCH = NQ / 64;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kKvOffBars);
+  uint64_t* bar_load = bars;
+  uint64_t* bar_s = bars + 1;
+  uint64_t* p_ready = bars + 2;
+  uint64_t* p_free = bars + 4;
+  uint64_t* bar_o = bars + 6;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
+  float* lse_s = reinterpret_cast<float*>(smem + kKvOffVec);
+  float* dl_s = lse_s + 256;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = heads * kHD;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  const int tile = blockIdx.x;
+  const int pair0 = S == 256 ? tile / 2 : tile * 2;
+  const int k_off = S == 256 ? (tile & 1) * 128 : 0;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_t);
+      tma_prefetch_desc(&tmap_all);
+      tma_prefetch_desc(&tmap_do_all);
+      mbar_init(bar_load, 1);
+      mbar_init(bar_s, 1);
+      mbar_init(bar_o, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&p_ready[i], 128);
+        mbar_init(&p_free[i], 1);
+      }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  float n_k = 1.f, n_v = 1.f;
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_load, 2 * kQBytes + 2 * NQ * 128);
+      if (S == 256) {
+        const int b = pair0 / heads, head = pair0 - b * heads;
+        tma_load_2d(smem + kKvOffK, &tmap_t, bar_load, C + head * kHD, b * S + k_off);
+        tma_load_2d(smem + kKvOffV, &tmap_t, bar_load, 2 * C + head * kHD, b * S + k_off);
+        tma_load_2d(smem + kKvOffQ, &tmap_all, bar_load, head * kHD, b * S);
+        tma_load_2d(smem + kKvOffDO, &tmap_do_all, bar_load, head * kHD, b * S);
+      } else {
+        for (int pp = 0; pp < 2; ++pp) {
+          int pair = pair0 + pp;
+          if (pair >= n_pairs) pair = n_pairs - 1;
+          const int b = pair / heads, head = pair - b * heads;
+          tma_load_2d(smem + kKvOffK + pp * 8192, &tmap_all, bar_load, C + head * kHD, b * S);
+          tma_load_2d(smem + kKvOffV + pp * 8192, &tmap_all, bar_load, 2 * C + head * kHD, b * S);
+          tma_load_2d(smem + kKvOffQ + pp * 8192, &tmap_all, bar_load, head * kHD, b * S);
+          tma_load_2d(smem + kKvOffDO + pp * 8192, &tmap_do_all, bar_load, head * kHD, b * S);
+        }
+      }
+    }
+  } else {
+    const int m = threadIdx.x;
+    // per-query log-sum-exp (log2 domain) and delta of every query this tile sees
+    for (int i = m; i < NQ; i += 128) {
+      const int pair = S == 256 ? pair0 : pair0 + (i >> 6);
+      const int pr = pair < n_pairs ? pair : n_pairs - 1;
+      const int qi = S == 256 ? i : (i & 63);
+      lse_s[i] = lse[(long long)pr * S + qi] * kLog2eA;
+      dl_s[i] = delta[(long long)pr * S + qi];
+    }
+    mbar_wait_bounded(bar_load, 0);
+    n_k = normalize_row_n(smem + kKvOffK, m);
+    n_v = normalize_row_n(smem + kKvOffV, m);
+    for (int r = m; r < NQ; r += 128) normalize_row(smem + kKvOffQ, r);
+    fence_proxy_async_smem();
+  }
+  __syncthreads();
+
+  if (warp == 4) {
+    if (lane == 0) {
+      tc_fence_after();
+      const uint32_t idesc_s = make_idesc_bf16(128, NQ, 0, 0);
+      {  // S^T = Kn Qn^T
+        const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem + kKvOffK), 0, 1024);
+        const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem + kKvOffQ), 0, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc_s, k != 0 ? 1u : 0u);
+      }
+      {  // dP^T = Vn dO^T
+        const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem + kKvOffV), 0, 1024);
+        const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem + kKvOffDO), 0, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + 256, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc_s, k != 0 ? 1u : 0u);
+      }
+      umma_commit(bar_s);
+      const uint32_t idesc_o = make_idesc_bf16(128, kHD, 0, 1);
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c) {
+        const int slot = c & 1;
+        mbar_wait_bounded(&p_ready[slot], (c >> 1) & 1);
+        tc_fence_after();
+        const uint64_t ap_desc = make_smem_desc_sw128(smem_u32(smem + kKvOffRingP + slot * kPChunkBytes), 0, 1024);
+        const uint64_t as_desc = make_smem_desc_sw128(smem_u32(smem + kKvOffRingS + slot * kPChunkBytes), 0, 1024);
+        const uint64_t bdo_desc = make_smem_desc_sw128(smem_u32(smem + kKvOffDO + c * 64 * 128), 64 * 128, 1024);
+        const uint64_t bq_desc = make_smem_desc_sw128(smem_u32(smem + kKvOffQ + c * 64 * 128), 64 * 128, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // dVn += P^T_c dO_c   -> columns [0, 64)
+          umma_bf16(tmem_base, ap_desc + (uint64_t)(k * 2), bdo_desc + (uint64_t)(k * 128), idesc_o, (c | k) != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // dKn += dS^T_c Qn_c  -> columns [256, 320)
+          umma_bf16(tmem_base + 256, as_desc + (uint64_t)(k * 2), bq_desc + (uint64_t)(k * 128), idesc_o, (c | k) != 0 ? 1u : 0u);
+        umma_commit(&p_free[slot]);
+      }
+      umma_commit(bar_o);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;                      // key row of the tile
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int qb = S == 256 ? 0 : (m >> 6) * 64;      // queries this key is seen by
+    const int qn = S == 256 ? NQ : 64;
+    const float sc = scale * kLog2eA;
+    mbar_wait_bounded(bar_s, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < NCH; ++c) {
+      const int slot = c & 1;
+      uint8_t* pbuf = smem + kKvOffRingP + slot * kPChunkBytes;
+      uint8_t* sbuf = smem + kKvOffRingS + slot * kPChunkBytes;
+      if (c >= 2) mbar_wait_bounded(&p_free[slot], ((c >> 1) - 1) & 1);
+      const bool on = (c * 64 >= qb) && (c * 64 < qb + qn);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (on) {
+          uint32_t rs[32], rp[32];
+          tmem_ld32(t_row + c * 64 + h * 32, rs);
+          tmem_ld32(t_row + 256 + c * 64 + h * 32, rp);
+          tmem_ld_wait();
+          const float* lq = lse_s + c * 64 + h * 32;
+          const float* dq_ = dl_s + c * 64 + h * 32;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float pv[8], dv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int i = g * 8 + e;
+              pv[e] = exp2f(fmaf(__uint_as_float(rs[i]), sc, -lq[i]));
+              dv[e] = pv[e] * (__uint_as_float(rp[i]) - dq_[i]) * scale;
+            }
+            uint4 o;
+            o.x = pack_bf16(pv[0], pv[1]); o.y = pack_bf16(pv[2], pv[3]); o.z = pack_bf16(pv[4], pv[5]); o.w = pack_bf16(pv[6], pv[7]);
+            *prow(pbuf, m, h * 4 + g) = o;
+            o.x = pack_bf16(dv[0], dv[1]); o.y = pack_bf16(dv[2], dv[3]); o.z = pack_bf16(dv[4], dv[5]); o.w = pack_bf16(dv[6], dv[7]);
+            *prow(sbuf, m, h * 4 + g) = o;
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            *prow(pbuf, m, h * 4 + g) = make_uint4(0, 0, 0, 0);
+            *prow(sbuf, m, h * 4 + g) = make_uint4(0, 0, 0, 0);
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&p_ready[slot]);
+    }
+    mbar_wait_bounded(bar_o, 0);
+    tc_fence_after();
+    const int pair = S == 256 ? pair0 : pair0 + (m >> 6);
+    const int s_idx = S == 256 ? k_off + m : (m & 63);
+    uint32_t g0[32], g1[32];
+    if (pair < n_pairs) {
+      const int b = pair / heads, head = pair - b * heads;
+      __nv_bfloat16* base = g_qkv + ((long long)b * S + s_idx) * 3 * C + head * kHD;
+      tmem_ld32(t_row + 256, g0);
+      tmem_ld32(t_row + 256 + 32, g1);
+      tmem_ld_wait();
+      norm_adjoint_store(g0, g1, smem + kKvOffK, m, n_k, base + C);
+      tmem_ld32(t_row, g0);
+      tmem_ld32(t_row + 32, g1);
+      tmem_ld_wait();
+      norm_adjoint_store(g0, g1, smem + kKvOffV, m, n_v, base + 2 * C);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int S>
+int launch_bwd_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* y, const __nv_bfloat16* g_y, const float* lse, float* delta,
+                  __nv_bfloat16* g_qkv, int B, int heads, cudaStream_t stream) {
+  const int C = heads * kHD;
+  CUtensorMap t_tile, t_all, t_do_tile, t_do_all;
+  {
+    uint64_t dims[2] = {(uint64_t)3 * C, (uint64_t)B * S};
+    uint64_t strides[1] = {(uint64_t)3 * C * 2};
+    uint32_t box_t[2] = {64, (uint32_t)(S == 256 ? 128 : 64)};
+    uint32_t box_a[2] = {64, (uint32_t)S};
+    if (encode_tmap(&t_tile, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, box_t, CU_TENSOR_MAP_SWIZZLE_128B) != 0) return -1;
+    if (encode_tmap(&t_all, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, box_a, CU_TENSOR_MAP_SWIZZLE_128B) != 0) return -1;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)C, (uint64_t)B * S};
+    uint64_t strides[1] = {(uint64_t)C * 2};
+    uint32_t box_t[2] = {64, (uint32_t)(S == 256 ? 128 : 64)};
+    uint32_t box_a[2] = {64, (uint32_t)S};
+    if (encode_tmap(&t_do_tile, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g_y, dims, strides, box_t, CU_TENSOR_MAP_SWIZZLE_128B) != 0) return -1;
+    if (encode_tmap(&t_do_all, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g_y, dims, strides, box_a, CU_TENSOR_MAP_SWIZZLE_128B) != 0) return -1;
+  }
+  static bool configured = false;
+  if (!configured) {
+    TEDM_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem));
+    TEDM_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmem));
+    configured = true;
+  }
+  const int n_pairs = B * heads;
+  const int grid = S == 256 ? n_pairs * 2 : (n_pairs + 1) / 2;
+  const float scale = 1.0f / sqrtf((float)kHD);
+  attn_bwd_dq_tc_kernel<S><<<grid, kThreadsB, kDqSmem, stream>>>(t_tile, t_all, t_do_tile, y, lse, delta, g_qkv, n_pairs, heads, scale);
+  TEDM_LAUNCH_CHECK();
+  attn_bwd_dkv_tc_kernel<S><<<grid, kThreadsB, kKvSmem, stream>>>(t_tile, t_all, t_do_all, lse, delta, g_qkv, n_pairs, heads, scale);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int S>
 int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* y, float* lse, int B, int heads, cudaStream_t stream) {
   const int C = heads * kHD;
@@ -297,6 +812,12 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* y, float* lse, int B, int
 }  // namespace
 
 bool attention_tc_supported(int S, int hd) { return hd == kHD && (S == 256 || S == 64); }
+
+int attention_backward_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* y, const __nv_bfloat16* g_y, const float* lse,
+                          float* delta, __nv_bfloat16* g_qkv, int B, int S, int heads, cudaStream_t stream) {
+  if (S == 256) return launch_bwd_tc<256>(qkv, y, g_y, lse, delta, g_qkv, B, heads, stream);
+  return launch_bwd_tc<64>(qkv, y, g_y, lse, delta, g_qkv, B, heads, stream);
+}
 
 int attention_forward_tc(const __nv_bfloat16* qkv, __nv_bfloat16* y, float* lse, int B, int S, int heads, cudaStream_t stream) {
   TEDM_CHECK((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,

@@ -138,6 +138,8 @@ int channel_dot(const ChannelDotArgs& a, cudaStream_t stream);
 // ---- attention_tc.cu: tcgen05/TMEM forward for head_dim 64, S in {64, 256} ----
 bool attention_tc_supported(int S, int hd);
 int attention_forward_tc(const __nv_bfloat16* qkv, __nv_bfloat16* y, float* lse, int B, int S, int heads, cudaStream_t stream);
+int attention_backward_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* y, const __nv_bfloat16* g_y, const float* lse,
+                          float* delta, __nv_bfloat16* g_qkv, int B, int S, int heads, cudaStream_t stream);
 
 // ---- attention.cu ----
 int attention_forward(const __nv_bfloat16* qkv, __nv_bfloat16* y, float* lse, int B, int S, int heads, int hd,
