@@ -123,6 +123,10 @@ int tedm_scalelong_forward(const float* mean, const float* w1, const float* w2, 
                            float* gain, int B, int C, int R, tedm_stream_t stream);
 int tedm_scalelong_backward(const float* d_gain, const float* gain, const float* h_pre, const float* w1, const float* w2,
                             float* d_pre2, float* d_hpre, float* d_mean, int B, int C, int R, tedm_stream_t stream);
+/* sample post-processing (callbacks.py:152-154, datamodule.denormalize): out[b,h,w,c] = uint8(clamp(x[b,c,h,w] * std[c] * 2
+ * + mean[c], 0, 1) * 255), x fp32 NCHW (the sampler's output), out uint8 NHWC (what PIL / the PNG writer consumes) */
+int tedm_to_uint8_images(const float* x, const float* mean, const float* std, void* out, int B, int C, int HW,
+                         tedm_stream_t stream);
 /* dL/dw_hat of both ScaleLong layers, ACCUMULATED into dw2 [C][R] and dw1 [R][C+1] (zero them first):
  * dw2 += d_pre2^T h,  dw1 += d_hpre^T aug  (autograd of networks.py:112-115) */
 int tedm_scalelong_wgrad(const float* d_pre2, const float* h, const float* d_hpre, const float* aug, float* dw2, float* dw1,

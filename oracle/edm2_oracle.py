@@ -441,3 +441,12 @@ def heun_solve(model: Callable, x0: Tensor, labels=None, num_steps=18, sigma_min
         if trajectory is not None:
             trajectory.append(x.clone())
     return x
+
+
+def to_uint8_images(x: Tensor, mean, std) -> Tensor:
+    """src/tinyedm/callbacks.py:152-154 (PreditionWriter.write_on_batch_end): denormalise, clamp, NHWC, * 255, uint8."""
+    mean = torch.as_tensor(mean, dtype=torch.float32).view(1, -1, 1, 1)
+    std = torch.as_tensor(std, dtype=torch.float32).view(1, -1, 1, 1)
+    images = x * std * 2 + mean
+    images = torch.clamp(images, 0, 1).permute(0, 2, 3, 1) * 255
+    return images.to(torch.uint8)

@@ -505,3 +505,17 @@ def test_imagenet_latent_config_forward_backward_vs_oracle(dev):
             worst = (k, r)
     print(f"ImageNet-latent config: D rel {rel(D, D_o):.2e}, worst tensor-gradient error {worst[1]:.2e} ({worst[0]})")
     assert worst[1] < 6e-2, worst
+
+
+def test_sample_postprocessing_uint8_bit_exact(dev):
+    """denormalise -> clamp -> NHWC -> uint8 on the device, byte-identical to callbacks.py:152-154."""
+    import tinyedm_b200 as T
+    g = torch.Generator().manual_seed(11)
+    for (B, C, H, W, mean, std) in [(16, 3, 32, 32, (0.4914, 0.4822, 0.4465), (0.247, 0.243, 0.261)), (5, 1, 28, 28, (0.1307,), (0.3081,)),
+                                    (3, 4, 64, 64, (0.1, 0.2, 0.3, 0.4), (0.5, 0.6, 0.7, 0.8))]:
+        x = torch.randn(B, C, H, W, generator=g) * 1.5
+        x.view(-1)[:8] = torch.tensor([0.0, 1e9, -1e9, 2.0, -2.0, 0.5, -0.5, 1.0])
+        got = T.to_uint8_images(x.to(dev), torch.tensor(mean), torch.tensor(std))
+        want = O.to_uint8_images(x, mean, std)
+        assert got.dtype == torch.uint8 and got.shape == (B, H, W, C)
+        assert torch.equal(got.cpu(), want)

@@ -8,8 +8,10 @@ from .edm import EDM, Diffuser
 from .graphs import GraphedTrainStep
 from .metric import WeightedMeanSquaredError, fused_edm_loss
 from .networks import Conv2d, Denoiser, DenoiserWrapper, Embedding, Linear, UncertaintyNet
+from .ops import to_uint8_images
 from .optim import FusedAdamEMA, sigma_rel_to_gamma
 from .solvers import DeterministicSolver
+from .utils import deinstantiate, instantiate, load_reference_checkpoint, swap_tensors
 
 __all__ = ["EDM", "Diffuser", "DeterministicSolver", "WeightedMeanSquaredError", "Denoiser", "Linear", "Conv2d",
-           "Embedding", "DenoiserWrapper", "UncertaintyNet", "FusedAdamEMA", "sigma_rel_to_gamma", "fused_edm_loss", "GraphedTrainStep"]
+           "Embedding", "DenoiserWrapper", "UncertaintyNet", "FusedAdamEMA", "sigma_rel_to_gamma", "fused_edm_loss", "GraphedTrainStep", "deinstantiate", "instantiate", "swap_tensors", "load_reference_checkpoint", "to_uint8_images"]

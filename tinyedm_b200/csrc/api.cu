@@ -133,6 +133,10 @@ int tedm_scalelong_backward(const float* d_gain, const float* gain, const float*
   ScaleLongBwdArgs a{d_gain, gain, h_pre, w1, w2, d_pre2, d_hpre, d_mean, B, C, R};
   return scalelong_backward(a, ST(stream));
 }
+int tedm_to_uint8_images(const float* x, const float* mean, const float* std, void* out, int B, int C, int HW,
+                         tedm_stream_t stream) {
+  return to_uint8_images(x, mean, std, static_cast<uint8_t*>(out), B, C, HW, ST(stream));
+}
 int tedm_scalelong_wgrad(const float* d_pre2, const float* h, const float* d_hpre, const float* aug, float* dw2, float* dw1,
                          int B, int C, int R, tedm_stream_t stream) {
   return scalelong_wgrad(d_pre2, h, d_hpre, aug, dw2, dw1, B, C, R, ST(stream));

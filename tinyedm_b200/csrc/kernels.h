@@ -233,6 +233,7 @@ struct ConvOutBwdArgs {
   int B, HW, C, Co;
 };
 int conv_out_backward(const ConvOutBwdArgs& a, cudaStream_t stream);
+int to_uint8_images(const float* x, const float* mean, const float* std, uint8_t* out, int B, int C, int HW, cudaStream_t stream);
 int wmse_forward(const float* D, const float* y, const float* sigma, const float* u, const float* weight, float sigma_data,
                  float* mse, float* wsum, float* loss, int B, int n, cudaStream_t stream);
 int wmse_backward(const float* D, const float* y, const float* sigma, const float* u, const float* weight, const float* mse,

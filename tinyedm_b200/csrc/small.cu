@@ -596,7 +596,35 @@ __global__ void diffuse_kernel(const float* __restrict__ clean, const float* __r
   noisy[i] = clean[i] + noise[i] * s;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Sample post-processing (callbacks.py:152-154): images = clamp(x * std * 2 + mean, 0, 1) -> NHWC -> * 255 -> uint8.
+// One thread per pixel; explicit round-to-nearest multiplies / adds in torch's operation order so the truncated byte
+// is bit-identical to the reference's (no FMA contraction).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+to_uint8_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ std,
+                uint8_t* __restrict__ out, int B, int C, int HW) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * HW) return;
+  const int b = (int)(i / HW), p = (int)(i - (long long)b * HW);
+  for (int c = 0; c < C; ++c) {
+    float v = __fadd_rn(__fmul_rn(__fmul_rn(x[((long long)b * C + c) * HW + p], std[c]), 2.0f), mean[c]);
+    v = fminf(fmaxf(v, 0.0f), 1.0f);
+    out[i * C + c] = (uint8_t)__fmul_rn(v, 255.0f);
+  }
+}
+
 }  // namespace
+
+int to_uint8_images(const float* x, const float* mean, const float* std, uint8_t* out, int B, int C, int HW,
+                    cudaStream_t stream) {
+  const long long n = (long long)B * HW;
+  if (n <= 0) return 0;
+  TEDM_CHECK(C >= 1 && C <= 16, "to_uint8_images: unsupported channel count %d", C);
+  to_uint8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, mean, std, out, B, C, HW);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
 
 int sgemm(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int transA, int transB,
           float alpha, float beta, cudaStream_t stream) {

@@ -9,7 +9,8 @@ reduction incl. lambda(sigma), exp(-u) and mean(u) (edm.py:212-219, metric.py:8-
 Adam(+EMA) kernel of tinyedm_b200.optim. When `lightning` is installed EDM derives from
 `lightning.LightningModule` exactly like the reference; without it (this image) it derives from `nn.Module` and
 `self.log` / `self.lr_schedulers` degrade to no-ops so the same step code runs under any plain training loop.
-Checkpoint plumbing (`load_from_checkpoint`, `save_config`, EMA callback wiring) is out of scope.
+`load_from_checkpoint` / `save_config` read and write the reference's checkpoint layout (tinyedm_b200/utils.py); the
+Lightning callback wiring around them is out of scope.
 """
 from __future__ import annotations
 
@@ -129,6 +130,18 @@ class EDM(_Base):
         class_label = class_label if self.conditional else None
         _, embedding = self.embedding(sigma, class_label)
         return self.denoiser(noisy_image, sigma, embedding)
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, *, map_location=None, load_ema: bool = False, **kwargs):
+        """edm.py:159-194: rebuilds the module from the checkpoint's `hyper_parameters` tree and loads its weights
+        (or the EMA weights kept in `optimizer_states[0]["ema"]`). Reads the reference's own checkpoints."""
+        from .utils import load_reference_checkpoint
+        return load_reference_checkpoint(checkpoint_path, load_ema=load_ema, map_location=map_location)
+
+    def save_config(self) -> dict:
+        """edm.py:154-157: the `deinstantiate` tree of this module (what the reference stores as `hyper_parameters`)."""
+        from .utils import deinstantiate
+        return deinstantiate(self)
 
     def prepare_weights(self, device) -> None:
         """Refreshes the cached normalised weights of the embedding and the denoiser (no-op while they are current);

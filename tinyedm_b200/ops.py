@@ -345,3 +345,16 @@ def diffuse(clean: Tensor, eps: Tensor, noise: Tensor, P_mean: float, P_std: flo
     _lib.call("tedm_diffuse", clean.data_ptr(), eps.data_ptr(), noise.data_ptr(), P_mean, P_std, noisy.data_ptr(),
               sigma.data_ptr(), B, n, _stream())
     return noisy, sigma
+
+
+def to_uint8_images(x: Tensor, mean: Tensor, std: Tensor) -> Tensor:
+    """(B,C,H,W) fp32 sampler output -> (B,H,W,C) uint8: clamp(x * std * 2 + mean, 0, 1) * 255 (callbacks.py:152-154)."""
+    check(x, F32, "images")
+    B, C, H, W = x.shape
+    mean = check(mean.to(x.device, F32).reshape(-1).contiguous(), F32, "mean")
+    std = check(std.to(x.device, F32).reshape(-1).contiguous(), F32, "std")
+    if mean.numel() != C or std.numel() != C:
+        raise RuntimeError(f"tinyedm_b200: mean/std must have {C} entries")
+    out = torch.empty((B, H, W, C), device=x.device, dtype=torch.uint8)
+    _lib.call("tedm_to_uint8_images", x.data_ptr(), mean.data_ptr(), std.data_ptr(), out.data_ptr(), B, C, H * W, _stream())
+    return out

@@ -71,6 +71,12 @@ class FusedAdamEMA(torch.optim.Optimizer):
         """EMA copies in `parameters()` order (the reference checkpoints them as `optimizer_states[0]["ema"]`)."""
         return tuple(self.state[p]["ema"] for p in self._params()) if self.gamma >= 0 else ()
 
+    def ema_state_dict(self) -> dict:
+        """The reference's `EMAOptimizer.state_dict()` layout (ema.py:326-336): what Lightning stores as
+        `optimizer_states[0]` and what `EDM.load_from_checkpoint(load_ema=True)` reads back."""
+        return {"opt": super().state_dict(), "ema": tuple(t.detach().clone() for t in self.ema_params),
+                "current_step": self.current_step, "gamma": self.gamma, "every_n_steps": 1}
+
     def _ensure_table(self, params) -> None:
         key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in params)
         if key == self._table_key:
