@@ -142,7 +142,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: role loops stay in uniform registers
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
 
@@ -171,64 +171,66 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t a_bytes = (uint32_t)p.NB * p.RH * p.W * kBlockK * 2;
-      const uint32_t tx_bytes = a_bytes + Cfg::kBTileBytes;
-      const int kc_per_tap = p.Cin / kBlockK;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        Tile t = decode_tile(p, tile);
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int dr = (p.taps == 9) ? tap / 3 - 1 : 0;
-          const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
-          for (int kc = 0; kc < kc_per_tap; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    const bool leader_lane = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t a_bytes = (uint32_t)p.NB * p.RH * p.W * kBlockK * 2;
+    const uint32_t tx_bytes = a_bytes + Cfg::kBTileBytes;
+    const int kc_per_tap = p.Cin / kBlockK;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      Tile t = decode_tile(p, tile);
+      for (int tap = 0; tap < p.taps; ++tap) {
+        const int dr = (p.taps == 9) ? tap / 3 - 1 : 0;
+        const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
+        for (int kc = 0; kc < kc_per_tap; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader_lane) {
             uint8_t* a_dst = smem + stage * Cfg::kStageBytes;
             uint8_t* b_dst = a_dst + kATileBytes;
             mbar_expect_tx(&full_bar[stage], tx_bytes);
             tma_load_4d(a_dst, &tmap_a, &full_bar[stage], kc * kBlockK, ds, t.h0 + dr, t.b0);
             tma_load_2d(b_dst, &tmap_b, &full_bar[stage], tap * p.Cin + kc * kBlockK, t.n0);
-            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        Tile t = decode_tile(p, tile);
-        int n_this = p.Cout - t.n0;
-        if (n_this > BN) n_this = BN;
-        const uint32_t idesc = make_idesc_bf16(kBlockM, n_this, 0, 0);
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    const bool leader_lane = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t smem_base = smem_u32(smem);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      Tile t = decode_tile(p, tile);
+      int n_this = p.Cout - t.n0;
+      if (n_this > BN) n_this = BN;
+      const uint32_t idesc = make_idesc_bf16(kBlockM, n_this, 0, 0);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t b_addr = a_addr + kATileBytes;
+        if (leader_lane) {
+          const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
           const uint64_t a_desc = make_smem_desc_sw128(a_addr, 0, 1024);
-          const uint64_t b_desc = make_smem_desc_sw128(b_addr, 0, 1024);
+          const uint64_t b_desc = make_smem_desc_sw128(a_addr + kATileBytes, 0, 1024);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // +32 bytes (encoded >>4) per 16-element K step inside the 128-byte swizzle row
-            umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
+      if (leader_lane) umma_commit(&tmem_full[acc]);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ===================== epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =====================

@@ -159,7 +159,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(in_full + 2);
   float* row_dots = reinterpret_cast<float*>(smem + kOffBars + 256);   // [2 halves][128 rows]
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: provably warp-uniform, so role branches and the producer / MMA loops below stay in
+  // uniform registers (the r1j profile showed the single MMA-issuing thread spending ~120 instructions per k block on
+  // R2UR / ELECT sequences and losing issue slots to the epilogue warps of its scheduler)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int cid = (int)cluster_id_x();
@@ -197,7 +200,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs): own 128 pixels of A, own half of the weight tile ==============
-    if (lane == 0) {
+    // The whole warp runs the (uniform) loop; one elected lane issues the barrier arrival and the TMA loads.
+    {
+      const bool leader_lane = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t a_bytes = (uint32_t)p.NB * p.RH * p.W * kBK * 2;
@@ -215,14 +220,17 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
           for (int kc = 0; kc < kc_per_tap; ++kc) {
             mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
-            uint8_t* a_dst = smem + stage * kStageBytes;
-            uint8_t* b_dst = a_dst + kATileBytes;
-            const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
-            // one arrival (the leader's) per phase; the peer's bytes only count towards the transaction total. They can
-            // never reach a stale phase: the peer refills a stage only after the MMAs that consumed it have completed.
-            if (rank == 0) mbar_expect_tx(&full_bar[stage], tx_pair);
-            tma_load_4d_pair(a_dst, &tmap_a, full_leader, kc * kBK, ds, t.h0 + dr, t.b0);
-            tma_load_2d_pair(b_dst, &tmap_b, full_leader, tap * p.Cin + kc * kBK, b_row);
+            if (leader_lane) {
+              uint8_t* a_dst = smem + stage * kStageBytes;
+              uint8_t* b_dst = a_dst + kATileBytes;
+              const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+              // one arrival (the leader's) per phase; the peer's bytes only count towards the transaction total. They can
+              // never reach a stale phase: the peer refills a stage only after the MMAs that consumed it have completed.
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], tx_pair);
+              tma_load_4d_pair(a_dst, &tmap_a, full_leader, kc * kBK, ds, t.h0 + dr, t.b0);
+              tma_load_2d_pair(b_dst, &tmap_b, full_leader, tap * p.Cin + kc * kBK, b_row);
+            }
+            __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -230,11 +238,14 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: one thread of the leader CTA drives both SMs' tensor cores ==================
-    if (rank == 0 && lane == 0) {
+    // Warp-uniform loop (all lanes wait on the barriers), one elected lane issues the MMAs and commits.
+    if (rank == 0) {
+      const bool leader_lane = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint32_t smem_base = smem_u32(smem);
       for (int ptile = cid; ptile < pair_tiles; ptile += ncl) {
         const int n0 = (ptile % p.n_tiles) * kBN;
         int n_this = p.Cout - n0;
@@ -246,16 +257,20 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait_bounded(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
-          const uint64_t a_desc = make_smem_desc_sw128(a_addr, 0, 1024);
-          const uint64_t b_desc = make_smem_desc_sw128(a_addr + kATileBytes, 0, 1024);
+          if (leader_lane) {
+            const uint32_t a_addr = smem_base + stage * kStageBytes;
+            const uint64_t a_desc = make_smem_desc_sw128(a_addr, 0, 1024);
+            const uint64_t b_desc = make_smem_desc_sw128(a_addr + kATileBytes, 0, 1024);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k)
-            umma_bf16_pair(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_pair(&empty_bar[stage]);
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16_pair(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage]);
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit_pair(&tmem_full[acc]);
+        if (leader_lane) umma_commit_pair(&tmem_full[acc]);
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

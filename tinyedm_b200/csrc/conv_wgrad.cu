@@ -55,7 +55,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
   const int kStageBytes = p.stage_bytes;
   const int kBoxBytesMax = p.rows * 128;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
 
   // work item decode
@@ -98,15 +98,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx = (uint32_t)(2 + n_boxes) * box_bytes;
-      for (int t = t_begin; t < t_end; ++t) {
-        const int bi = t / p.tiles_h;
-        const int b0 = bi * p.NB;
-        const int h0 = (t - bi * p.tiles_h) * p.RH;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+    const bool leader_lane = elect_one();   // warp-uniform loop, one elected lane issues
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx = (uint32_t)(2 + n_boxes) * box_bytes;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int bi = t / p.tiles_h;
+      const int b0 = bi * p.NB;
+      const int h0 = (t - bi * p.tiles_h) * p.RH;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (leader_lane) {
         uint8_t* s = smem + stage * kStageBytes;
         mbar_expect_tx(&full_bar[stage], tx);
         tma_load_4d(s, &tmap_g, &full_bar[stage], co0, 0, h0, b0);
@@ -114,34 +115,37 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
         uint8_t* xs = s + 2 * kBoxBytesMax;
         for (int j = 0; j < n_boxes; ++j)
           tma_load_4d(xs + j * box_bytes, &tmap_x, &full_bar[stage], ci0 + j * 64, ds, h0 + dr, b0);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t idesc = make_idesc_bf16(kBM, n_this, 1, 1);
-      const int ksteps = p.rows / 16;
-      bool first = true;
-      for (int t = t_begin; t < t_end; ++t) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+    const bool leader_lane = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t idesc = make_idesc_bf16(kBM, n_this, 1, 1);
+    const int ksteps = p.rows / 16;
+    const uint32_t smem_base = smem_u32(smem);
+    uint32_t accumulate = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (leader_lane) {
+        const uint32_t a_addr = smem_base + stage * kStageBytes;
         const uint32_t b_addr = a_addr + 2 * kBoxBytesMax;
         const uint64_t a_desc = make_smem_desc_sw128(a_addr, box_bytes, 1024);
         const uint64_t b_desc = make_smem_desc_sw128(b_addr, box_bytes, 1024);
         for (int k = 0; k < ksteps; ++k) {
-          // 16 pixels (K) = 16 rows of 128 B = 2048 B
-          umma_bf16(tmem_base, a_desc + (uint64_t)(k * 128), b_desc + (uint64_t)(k * 128), idesc,
-                    first ? 0u : 1u);
-          first = false;
+          umma_bf16(tmem_base, a_desc + (uint64_t)(k * 128), b_desc + (uint64_t)(k * 128), idesc, accumulate);
+          accumulate = 1;
         }
         umma_commit(&empty_bar[stage]);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(acc_full);
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
+    if (leader_lane) umma_commit(acc_full);
+    __syncwarp();
   } else if (warp >= 4) {
     const int q = warp & 3;
     const int co = co0 + q * 32 + lane;
@@ -240,7 +244,7 @@ conv_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
   const int kStages = p.stages;
   const int kStageBytes = p.stage_bytes;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform (see conv_pair.cu)
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int cl = (int)cluster_id_x();
@@ -286,15 +290,17 @@ conv_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx_pair = 2u * (uint32_t)(2 + nb_half) * box_bytes;
-      for (int t = t_begin; t < t_end; ++t) {
-        const int bi = t / p.tiles_h;
-        const int b0 = bi * p.NB;
-        const int h0 = (t - bi * p.tiles_h) * p.RH;
-        mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
+    // warp-uniform loop, one elected lane issues (keeps the loop state in uniform registers)
+    const bool leader_lane = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx_pair = 2u * (uint32_t)(2 + nb_half) * box_bytes;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int bi = t / p.tiles_h;
+      const int b0 = bi * p.NB;
+      const int h0 = (t - bi * p.tiles_h) * p.RH;
+      mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
+      if (leader_lane) {
         uint8_t* s = smem + stage * kStageBytes;
         const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
         if (rank == 0) mbar_expect_tx(&full_bar[stage], tx_pair);
@@ -303,31 +309,38 @@ conv_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         uint8_t* xs = s + 2 * box_bytes;
         for (int j = 0; j < nb_half; ++j)
           tma_load_4d_pair(xs + j * box_bytes, &tmap_x, full_leader, ci0 + (int)rank * (n_this >> 1) + j * 64, ds, h0 + dr, b0);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (rank == 0 && lane == 0) {
+    if (rank == 0) {
+      const bool leader_lane = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t idesc = make_idesc_bf16(256, n_this, 1, 1);
       const int ksteps = p.rows / 16;
-      bool first = true;
+      const uint32_t smem_base = smem_u32(smem);
+      uint32_t accumulate = 0;
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait_bounded(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
-        const uint32_t b_addr = a_addr + 2 * box_bytes;
-        const uint64_t a_desc = make_smem_desc_sw128(a_addr, box_bytes, 1024);
-        const uint64_t b_desc = make_smem_desc_sw128(b_addr, box_bytes, 1024);
-        for (int k = 0; k < ksteps; ++k) {
-          umma_bf16_pair(tmem_base, a_desc + (uint64_t)(k * 128), b_desc + (uint64_t)(k * 128), idesc, first ? 0u : 1u);
-          first = false;
+        if (leader_lane) {
+          const uint32_t a_addr = smem_base + stage * kStageBytes;
+          const uint32_t b_addr = a_addr + 2 * box_bytes;
+          const uint64_t a_desc = make_smem_desc_sw128(a_addr, box_bytes, 1024);
+          const uint64_t b_desc = make_smem_desc_sw128(b_addr, box_bytes, 1024);
+          for (int k = 0; k < ksteps; ++k) {
+            umma_bf16_pair(tmem_base, a_desc + (uint64_t)(k * 128), b_desc + (uint64_t)(k * 128), idesc, accumulate);
+            accumulate = 1;
+          }
+          umma_commit_pair(&empty_bar[stage]);
         }
-        umma_commit_pair(&empty_bar[stage]);
+        __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit_pair(acc_full);
+      if (leader_lane) umma_commit_pair(acc_full);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // epilogue: 128 rows (co) x n_this columns (ci) of fp32 -> swizzled [128][32] chunks -> TMA reduce-add / store
