@@ -81,7 +81,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint64_t* p_free = bars + 4;        // [2] the MMAs reading ring slot have completed
   uint64_t* bar_o = bars + 6;         // O in TMEM
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // uniform warp index
   const int C = heads * kHD;
   if ((smem_u32(smem) & 1023u) != 0) __trap();      // the swizzled tiles need a 1024-byte aligned base
   // tile -> (first pair, query offset)
@@ -280,14 +280,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 //               bf16 rings -> dVn += P^T dO, dKn += dS^T Qn
 // Each result row then goes through the adjoint of its pixel norm  g_u = g/n - y (g.y) / ((n - eps) hd)  in registers.
 // =====================================================================================================================
-constexpr int kThreadsB = 160;
-// dq: Q tile 16K | dO tile 16K | K 32K | V 32K | dS ring 2 x 16K
-constexpr int kDqOffQ = 0, kDqOffDO = 16384, kDqOffK = 32768, kDqOffV = 65536, kDqOffRing = 98304, kDqOffBars = 131072;
+// 8 compute warps (two per TMEM lane quarter: "sub" 0/1 split the 64-key chunks) + 1 TMA/MMA warp. One compute warp per
+// scheduler (the first version) was latency bound: ~3 700 dependent instructions per thread and nothing to hide them.
+constexpr int kThreadsB = 288;
+// dq: Q tile 16K | dO tile 16K | K 32K | V 32K | dS ring 4 x 16K (one slot per key chunk: no slot recycling)
+constexpr int kDqOffQ = 0, kDqOffDO = 16384, kDqOffK = 32768, kDqOffV = 65536, kDqOffRing = 98304, kDqOffBars = 163840;
 constexpr int kDqSmem = kDqOffBars + 128;
-// dkv: K tile 16K | V tile 16K | Q 32K | dO 32K | P^T ring 2 x 16K | dS^T ring 2 x 16K | lse2[256] | delta[256]
-constexpr int kKvOffK = 0, kKvOffV = 16384, kKvOffQ = 32768, kKvOffDO = 65536, kKvOffRingP = 98304, kKvOffRingS = 131072,
-              kKvOffVec = 163840, kKvOffBars = 163840 + 2048;
+// dkv: K tile 16K | V tile 16K | Q 32K | dO 32K | P^T ring 4 x 16K | dS^T ring 4 x 16K | lse2[256] | delta[256]
+constexpr int kKvOffK = 0, kKvOffV = 16384, kKvOffQ = 32768, kKvOffDO = 65536, kKvOffRingP = 98304, kKvOffRingS = 163840,
+              kKvOffVec = 229376, kKvOffBars = 229376 + 2048;
 constexpr int kKvSmem = kKvOffBars + 128;
+static_assert(kKvSmem <= 232448, "shared memory budget");
 
 // pixel-norm adjoint of one 64-element gradient row held as two 32-float halves; y = the normalised row in a swizzled slab
 __device__ __forceinline__ void norm_adjoint_store(const uint32_t (&g0)[32], const uint32_t (&g1)[32], uint8_t* slab, int r,
@@ -359,18 +362,17 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDqOffBars);
   uint64_t* bar_load = bars;
   uint64_t* bar_s = bars + 1;
-  uint64_t* p_ready = bars + 2;   // [2]
-  uint64_t* p_free = bars + 4;    // [2]
+  uint64_t* p_ready = bars + 2;   // [4] one per key chunk
   uint64_t* bar_o = bars + 6;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // uniform warp index
   const int C = heads * kHD;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   const int tile = blockIdx.x;
   const int pair0 = S == 256 ? tile / 2 : tile * 2;
   const int q_off = S == 256 ? (tile & 1) * kTileQ : 0;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tmap_q);
       tma_prefetch_desc(&tmap_kv);
@@ -378,10 +380,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       mbar_init(bar_load, 1);
       mbar_init(bar_s, 1);
       mbar_init(bar_o, 1);
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&p_ready[i], 128);
-        mbar_init(&p_free[i], 1);
-      }
+      for (int i = 0; i < 4; ++i) mbar_init(&p_ready[i], 128);
       mbar_fence_init();
     }
     __syncwarp();
@@ -394,7 +393,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   const uint32_t tmem_base = *tmem_ptr;
 
   float n_q = 1.f, dl = 0.f, ls2 = 0.f;
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_expect_tx(bar_load, 2 * kQBytes + 2 * NK * 128);
       if (S == 256) {
@@ -416,7 +415,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       }
     }
   } else {
-    const int m = threadIdx.x;
+    const int m = threadIdx.x & 127;            // query row of this thread (both subs own the same rows)
+    const int sub = threadIdx.x >> 7;
     const int pair = S == 256 ? pair0 : pair0 + (m >> 6);
     const int s_idx = S == 256 ? q_off + m : (m & 63);
     const bool live = pair < n_pairs;
@@ -438,9 +438,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       acc += g0.x * o0.x + g0.y * o0.y + g1.x * o1.x + g1.y * o1.y + g2.x * o2.x + g2.y * o2.y + g3.x * o3.x + g3.y * o3.y;
     }
     dl = acc;
-    if (live) delta[(long long)pair * S + s_idx] = acc;
-    n_q = normalize_row_n(smem + kDqOffQ, m);
-    for (int r = m; r < NK; r += 128) {
+    if (live && sub == 0) delta[(long long)pair * S + s_idx] = acc;
+    if (sub == 0) n_q = normalize_row_n(smem + kDqOffQ, m);
+    for (int r = threadIdx.x; r < NK; r += 256) {
       normalize_row(smem + kDqOffK, r);
       normalize_row(smem + kDqOffV, r);
     }
@@ -448,7 +448,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   }
   __syncthreads();
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       tc_fence_after();
       const uint32_t idesc_s = make_idesc_bf16(128, NK, 0, 0);
@@ -470,20 +470,19 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       const uint32_t idesc_o = make_idesc_bf16(128, kHD, 0, 1);
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
-        const int slot = c & 1;
-        mbar_wait_bounded(&p_ready[slot], (c >> 1) & 1);
+        mbar_wait_bounded(&p_ready[c], 0);
         tc_fence_after();
-        const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem + kDqOffRing + slot * kPChunkBytes), 0, 1024);
+        const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem + kDqOffRing + c * kPChunkBytes), 0, 1024);
         const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem + kDqOffK + c * 64 * 128), 64 * 128, 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 128), idesc_o, (c | k) != 0 ? 1u : 0u);
-        umma_commit(&p_free[slot]);
       }
       umma_commit(bar_o);
     }
   } else {
     const int q = warp & 3;
+    const int sub = warp >> 2;                     // which half of the key chunks this warp handles
     const int m = q * 32 + lane;
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
     const int kb = S == 256 ? 0 : (m >> 6) * 64;
@@ -492,10 +491,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     mbar_wait_bounded(bar_s, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < NCH; ++c) {
-      const int slot = c & 1;
-      uint8_t* pbuf = smem + kDqOffRing + slot * kPChunkBytes;
-      if (c >= 2) mbar_wait_bounded(&p_free[slot], ((c >> 1) - 1) & 1);
+    for (int c = sub * (NCH / 2); c < (sub + 1) * (NCH / 2); ++c) {
+      uint8_t* pbuf = smem + kDqOffRing + c * kPChunkBytes;
       const bool on = (c * 64 >= kb) && (c * 64 < kb + kn);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -522,7 +519,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(&p_ready[slot]);
+      mbar_arrive(&p_ready[c]);
     }
     mbar_wait_bounded(bar_o, 0);
     tc_fence_after();
@@ -532,14 +529,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     tmem_ld32(t_row, g0);
     tmem_ld32(t_row + 32, g1);
     tmem_ld_wait();
-    if (pair < n_pairs) {
+    if (pair < n_pairs && sub == 0) {
       const int b = pair / heads, head = pair - b * heads;
       norm_adjoint_store(g0, g1, smem + kDqOffQ, m, n_q, g_qkv + ((long long)b * S + s_idx) * 3 * C + head * kHD);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -557,20 +554,19 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kKvOffBars);
   uint64_t* bar_load = bars;
   uint64_t* bar_s = bars + 1;
-  uint64_t* p_ready = bars + 2;
-  uint64_t* p_free = bars + 4;
+  uint64_t* p_ready = bars + 2;   // [4] one per query chunk
   uint64_t* bar_o = bars + 6;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
   float* lse_s = reinterpret_cast<float*>(smem + kKvOffVec);
   float* dl_s = lse_s + 256;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // uniform warp index
   const int C = heads * kHD;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   const int tile = blockIdx.x;
   const int pair0 = S == 256 ? tile / 2 : tile * 2;
   const int k_off = S == 256 ? (tile & 1) * 128 : 0;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tmap_t);
       tma_prefetch_desc(&tmap_all);
@@ -578,10 +574,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_
       mbar_init(bar_load, 1);
       mbar_init(bar_s, 1);
       mbar_init(bar_o, 1);
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&p_ready[i], 128);
-        mbar_init(&p_free[i], 1);
-      }
+      for (int i = 0; i < 4; ++i) mbar_init(&p_ready[i], 128);
       mbar_fence_init();
     }
     __syncwarp();
@@ -594,7 +587,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_
   const uint32_t tmem_base = *tmem_ptr;
 
   float n_k = 1.f, n_v = 1.f;
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_expect_tx(bar_load, 2 * kQBytes + 2 * NQ * 128);
       if (S == 256) {
@@ -616,9 +609,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_
       }
     }
   } else {
-    const int m = threadIdx.x;
+    const int m = threadIdx.x & 127;            // key row of this thread (both subs own the same rows)
+    const int sub = threadIdx.x >> 7;
     // per-query log-sum-exp (log2 domain) and delta of every query this tile sees
-    for (int i = m; i < NQ; i += 128) {
+    for (int i = threadIdx.x; i < NQ; i += 256) {
       const int pair = S == 256 ? pair0 : pair0 + (i >> 6);
       const int pr = pair < n_pairs ? pair : n_pairs - 1;
       const int qi = S == 256 ? i : (i & 63);
@@ -626,14 +620,14 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_
       dl_s[i] = delta[(long long)pr * S + qi];
     }
     mbar_wait_bounded(bar_load, 0);
-    n_k = normalize_row_n(smem + kKvOffK, m);
-    n_v = normalize_row_n(smem + kKvOffV, m);
-    for (int r = m; r < NQ; r += 128) normalize_row(smem + kKvOffQ, r);
+    if (sub == 0) n_k = normalize_row_n(smem + kKvOffK, m);   // sub 0 owns the dK epilogue, sub 1 the dV epilogue
+    else n_v = normalize_row_n(smem + kKvOffV, m);
+    for (int r = threadIdx.x; r < NQ; r += 256) normalize_row(smem + kKvOffQ, r);
     fence_proxy_async_smem();
   }
   __syncthreads();
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       tc_fence_after();
       const uint32_t idesc_s = make_idesc_bf16(128, NQ, 0, 0);
@@ -655,11 +649,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_
       const uint32_t idesc_o = make_idesc_bf16(128, kHD, 0, 1);
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
-        const int slot = c & 1;
-        mbar_wait_bounded(&p_ready[slot], (c >> 1) & 1);
+        mbar_wait_bounded(&p_ready[c], 0);
         tc_fence_after();
-        const uint64_t ap_desc = make_smem_desc_sw128(smem_u32(smem + kKvOffRingP + slot * kPChunkBytes), 0, 1024);
-        const uint64_t as_desc = make_smem_desc_sw128(smem_u32(smem + kKvOffRingS + slot * kPChunkBytes), 0, 1024);
+        const uint64_t ap_desc = make_smem_desc_sw128(smem_u32(smem + kKvOffRingP + c * kPChunkBytes), 0, 1024);
+        const uint64_t as_desc = make_smem_desc_sw128(smem_u32(smem + kKvOffRingS + c * kPChunkBytes), 0, 1024);
         const uint64_t bdo_desc = make_smem_desc_sw128(smem_u32(smem + kKvOffDO + c * 64 * 128), 64 * 128, 1024);
         const uint64_t bq_desc = make_smem_desc_sw128(smem_u32(smem + kKvOffQ + c * 64 * 128), 64 * 128, 1024);
 #pragma unroll
@@ -668,12 +661,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // dKn += dS^T_c Qn_c  -> columns [256, 320)
           umma_bf16(tmem_base + 256, as_desc + (uint64_t)(k * 2), bq_desc + (uint64_t)(k * 128), idesc_o, (c | k) != 0 ? 1u : 0u);
-        umma_commit(&p_free[slot]);
       }
       umma_commit(bar_o);
     }
   } else {
     const int q = warp & 3;
+    const int sub = warp >> 2;                        // which half of the query chunks this warp handles
     const int m = q * 32 + lane;                      // key row of the tile
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
     const int qb = S == 256 ? 0 : (m >> 6) * 64;      // queries this key is seen by
@@ -682,11 +675,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_
     mbar_wait_bounded(bar_s, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < NCH; ++c) {
-      const int slot = c & 1;
-      uint8_t* pbuf = smem + kKvOffRingP + slot * kPChunkBytes;
-      uint8_t* sbuf = smem + kKvOffRingS + slot * kPChunkBytes;
-      if (c >= 2) mbar_wait_bounded(&p_free[slot], ((c >> 1) - 1) & 1);
+    for (int c = sub * (NCH / 2); c < (sub + 1) * (NCH / 2); ++c) {
+      uint8_t* pbuf = smem + kKvOffRingP + c * kPChunkBytes;
+      uint8_t* sbuf = smem + kKvOffRingS + c * kPChunkBytes;
       const bool on = (c * 64 >= qb) && (c * 64 < qb + qn);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -722,7 +713,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(&p_ready[slot]);
+      mbar_arrive(&p_ready[c]);
     }
     mbar_wait_bounded(bar_o, 0);
     tc_fence_after();
@@ -732,19 +723,22 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_
     if (pair < n_pairs) {
       const int b = pair / heads, head = pair - b * heads;
       __nv_bfloat16* base = g_qkv + ((long long)b * S + s_idx) * 3 * C + head * kHD;
-      tmem_ld32(t_row + 256, g0);
-      tmem_ld32(t_row + 256 + 32, g1);
-      tmem_ld_wait();
-      norm_adjoint_store(g0, g1, smem + kKvOffK, m, n_k, base + C);
-      tmem_ld32(t_row, g0);
-      tmem_ld32(t_row + 32, g1);
-      tmem_ld_wait();
-      norm_adjoint_store(g0, g1, smem + kKvOffV, m, n_v, base + 2 * C);
+      if (sub == 0) {
+        tmem_ld32(t_row + 256, g0);
+        tmem_ld32(t_row + 256 + 32, g1);
+        tmem_ld_wait();
+        norm_adjoint_store(g0, g1, smem + kKvOffK, m, n_k, base + C);
+      } else {
+        tmem_ld32(t_row, g0);
+        tmem_ld32(t_row + 32, g1);
+        tmem_ld_wait();
+        norm_adjoint_store(g0, g1, smem + kKvOffV, m, n_v, base + 2 * C);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
