@@ -419,9 +419,9 @@ def run_b200(args) -> None:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (conv_pair_kernel, 3x3 256->256 @32x32,
-# B=256) from the committed `ncu --set full` capture profiles/r1h_conv_pair_ncu_full.md: mean of the two captured
-# flavours (modulation-silu 347.8 MB, mp_add 376.8 MB); algorithmic bytes are 402-403 MB per launch.
-TRAFFIC_BYTES = 362.3e6
+# B=256) from the committed `ncu --set full` capture profiles/r1k_conv_pair_ncu_full.md: launch-weighted mean over the
+# four flavours of a training step (347 / 377 / 375 / 517 MB at 9 : 18 : 18 : 9); algorithmic bytes 402-537 MB per launch.
+TRAFFIC_BYTES = 394.8e6
 
 
 def main() -> None:

@@ -22,3 +22,8 @@ for _ in range(2):
     ops.conv2d(x, wq, 3, C, out=out, epi=EPI_SILU_BWD, aux=res, res=raw, beta=0.6, nrm=nrm, block_n=bn if bn == 0 else 256)
 torch.cuda.synchronize()
 print("done")
+# weight gradient of the same shape (CTA-pair kernel)
+dw = torch.zeros(C, 9, C, device=dev)
+for _ in range(2):
+    ops.conv2d_wgrad(res, x, dw, 3)
+torch.cuda.synchronize()
