@@ -84,6 +84,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // uniform warp index
   const int C = heads * kHD;
   if ((smem_u32(smem) & 1023u) != 0) __trap();      // the swizzled tiles need a 1024-byte aligned base
+  if (threadIdx.x == 0) pdl_trigger();
   // tile -> (first pair, query offset)
   const int tile = blockIdx.x;
   const int pair0 = S == 256 ? tile / TILES_PER_PAIR : tile * 2;
@@ -368,6 +369,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // uniform warp index
   const int C = heads * kHD;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (threadIdx.x == 0) pdl_trigger();
   const int tile = blockIdx.x;
   const int pair0 = S == 256 ? tile / 2 : tile * 2;
   const int q_off = S == 256 ? (tile & 1) * kTileQ : 0;
@@ -562,6 +564,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // uniform warp index
   const int C = heads * kHD;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (threadIdx.x == 0) pdl_trigger();
   const int tile = blockIdx.x;
   const int pair0 = S == 256 ? tile / 2 : tile * 2;
   const int k_off = S == 256 ? (tile & 1) * 128 : 0;

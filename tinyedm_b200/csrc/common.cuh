@@ -37,6 +37,7 @@ int fail(const char* fmt, ...);  // sets the message, returns -1
   } while (0)
 
 int num_sms();
+bool pdl_enabled();   // TEDM_PDL=0 disables programmatic dependent launches (A/B switch)
 const char* last_error();
 
 // Encodes a tiled TMA descriptor through the driver entry point (resolved at run time so the
@@ -192,6 +193,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+// ----- programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may start
+// while its predecessor in the stream is still draining; everything before pdl_wait() (barrier init, TMEM allocation,
+// descriptor prefetch) overlaps the predecessor's tail, everything after sees all of its memory operations -----
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ----- CTA pair (cluster of 2, tcgen05 cta_group::2) -----
 __device__ __forceinline__ uint32_t cluster_ctarank() {

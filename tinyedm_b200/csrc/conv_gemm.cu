@@ -165,9 +165,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tmem_alloc(tmem_ptr, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  pdl_wait();                       // programmatic dependent launch: the prologue above overlaps the previous kernel's tail
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (threadIdx.x == 0) pdl_trigger();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
@@ -438,8 +440,17 @@ int launch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const ConvGemmParam
   }
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
-  conv_gemm_kernel<BN, EPI><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
-  TEDM_LAUNCH_CHECK();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  TEDM_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, EPI>, ta, tb, p));
   return 0;
 }
 

@@ -193,9 +193,14 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tmem_alloc_pair(tmem_ptr, kTmemCols);
     tmem_relinquish_pair();
   }
+  // Everything above (descriptor prefetch, barrier init, TMEM allocation) may overlap the tail of the previous kernel in
+  // the stream (programmatic dependent launch); from here on its results are visible. Our own dependents may be
+  // scheduled as soon as every CTA of this grid is running: they park in their prologue until this grid has finished.
+  pdl_wait();
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
+  if (threadIdx.x == 0) pdl_trigger();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
@@ -668,9 +673,17 @@ int launch_pair(const CUtensorMap* maps, const ConvGemmParams& p, int clusters, 
     TEDM_CUDA(cudaFuncSetAttribute(conv_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     configured = true;
   }
-  conv_pair_kernel<EPI><<<2 * clusters, kThreads, kSmemBytes, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4],
-                                                                       maps[5], p);
-  TEDM_LAUNCH_CHECK();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  TEDM_CUDA(cudaLaunchKernelEx(&cfg, conv_pair_kernel<EPI>, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p));
   return 0;
 }
 

@@ -284,9 +284,11 @@ conv_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
     tmem_alloc_pair(tmem_ptr, kBN);
     tmem_relinquish_pair();
   }
+  pdl_wait();                      // programmatic dependent launch: the prologue above overlaps the previous kernel's tail
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
+  if (threadIdx.x == 0) pdl_trigger();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
@@ -453,8 +455,17 @@ int conv_wgrad_pair_launch(const ConvWgradArgs& a, cudaStream_t stream) {
     TEDM_CUDA(cudaFuncSetAttribute(conv_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
     configured = true;
   }
-  conv_wgrad_pair_kernel<<<2 * p.items * splits, kPairThreads, kPairSmemBytes, stream>>>(tg, tx, tdw, p);
-  TEDM_LAUNCH_CHECK();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * p.items * splits);
+  cfg.blockDim = dim3(kPairThreads);
+  cfg.dynamicSmemBytes = kPairSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  TEDM_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_pair_kernel, tg, tx, tdw, p));
   return 0;
 }
 

@@ -59,6 +59,7 @@ __device__ __forceinline__ Vec8 load8f(const float* p) {
 template <int NV, int PU, bool kPool>
 __global__ void __launch_bounds__(256, (NV * PU <= 4) ? 4 : 2)
 block_prep_fwd_kernel(const PrepArgs a) {
+  pdl_trigger();   // a following tcgen05 kernel may run its prologue during this kernel's last wave
   const int H = a.resample == 1 ? a.Hin / 2 : (a.resample == 2 ? a.Hin * 2 : a.Hin);
   const int W = a.resample == 1 ? a.Win / 2 : (a.resample == 2 ? a.Win * 2 : a.Win);
   const int C = a.C1 + a.C2;
@@ -250,6 +251,7 @@ __device__ __forceinline__ void prep_bwd_store(const PrepBwdArgs& a, int b, long
 template <int NV>
 __global__ void __launch_bounds__(256)
 block_prep_bwd_kernel(const PrepBwdArgs a) {
+  pdl_trigger();   // a following tcgen05 kernel may run its prologue during this kernel's last wave
   const int H = a.resample == 1 ? a.Hin / 2 : (a.resample == 2 ? a.Hin * 2 : a.Hin);
   const int W = a.resample == 1 ? a.Win / 2 : (a.resample == 2 ? a.Win * 2 : a.Win);
   const int C = a.C1 + a.C2;
@@ -317,6 +319,7 @@ block_prep_bwd_kernel(const PrepBwdArgs a) {
 template <int NV, int PU, bool kUp>
 __global__ void __launch_bounds__(256, (NV * PU <= 4 && !kUp) ? 3 : 2)
 block_prep_bwd_light_kernel(const PrepBwdArgs a) {
+  pdl_trigger();   // a following tcgen05 kernel may run its prologue during this kernel's last wave
   const int C = a.C1 + a.C2;
   const int nvec = C / 8;
   const int lane = threadIdx.x & 31;
@@ -509,6 +512,7 @@ modsilu_bwd_kernel(const ModSiluBwdArgs a) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 4)
 channel_dot_kernel(const ChannelDotArgs a) {
+  pdl_trigger();   // a following tcgen05 kernel may run its prologue during this kernel's last wave
   extern __shared__ float sred[];
   const int nvec = a.C / 8;
   const int rows = blockDim.x / nvec;

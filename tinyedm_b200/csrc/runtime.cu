@@ -1,6 +1,7 @@
 // Host runtime glue: per-thread error message, SM count, TMA descriptor encoding via the driver
 // entry point (no link-time dependency on libcuda).
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <mutex>
 
@@ -38,6 +39,15 @@ int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("TEDM_PDL");
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
