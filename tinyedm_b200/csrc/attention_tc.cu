@@ -768,11 +768,10 @@ int launch_bwd_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* y, const __nv_b
     if (encode_tmap(&t_do_tile, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g_y, dims, strides, box_t, CU_TENSOR_MAP_SWIZZLE_128B) != 0) return -1;
     if (encode_tmap(&t_do_all, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g_y, dims, strides, box_a, CU_TENSOR_MAP_SWIZZLE_128B) != 0) return -1;
   }
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(&configured)) {
     TEDM_CUDA(cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem));
     TEDM_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKvSmem));
-    configured = true;
   }
   const int n_pairs = B * heads;
   const int grid = S == 256 ? n_pairs * 2 : (n_pairs + 1) / 2;
@@ -794,10 +793,9 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* y, float* lse, int B, int
   uint32_t box_kv[2] = {64, (uint32_t)S};                          // all keys of a head
   if (encode_tmap(&tq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, box_q, CU_TENSOR_MAP_SWIZZLE_128B) != 0) return -1;
   if (encode_tmap(&tkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, box_kv, CU_TENSOR_MAP_SWIZZLE_128B) != 0) return -1;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(&configured)) {
     TEDM_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesA));
-    configured = true;
   }
   const int n_pairs = B * heads;
   const int grid = S == 256 ? n_pairs * 2 : (n_pairs + 1) / 2;

@@ -37,7 +37,10 @@ int fail(const char* fmt, ...);  // sets the message, returns -1
   } while (0)
 
 int num_sms();
-bool pdl_enabled();   // TEDM_PDL=0 disables programmatic dependent launches (A/B switch)
+bool pdl_enabled();
+// True the first time it is called for (this flag word, current device): kernel attributes such as the dynamic
+// shared-memory limit are per device, and a process may drive more than one.
+bool first_use_on_device(unsigned long long* device_mask);   // TEDM_PDL=0 disables programmatic dependent launches (A/B switch)
 const char* last_error();
 
 // Encodes a tiled TMA descriptor through the driver entry point (resolved at run time so the

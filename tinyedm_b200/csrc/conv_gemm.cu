@@ -432,11 +432,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 template <int BN, int EPI>
 int launch_epi(const CUtensorMap& ta, const CUtensorMap& tb, const ConvGemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(&configured)) {
     TEDM_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::kSmemBytes));
-    configured = true;
   }
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();

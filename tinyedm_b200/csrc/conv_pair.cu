@@ -668,10 +668,9 @@ int weight_tmap(CUtensorMap* out, const void* base, int K, int Cout, int box_row
 
 template <int EPI>
 int launch_pair(const CUtensorMap* maps, const ConvGemmParams& p, int clusters, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(&configured)) {
     TEDM_CUDA(cudaFuncSetAttribute(conv_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    configured = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * clusters);

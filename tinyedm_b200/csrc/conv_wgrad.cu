@@ -450,10 +450,9 @@ int conv_wgrad_pair_launch(const ConvWgradArgs& a, cudaStream_t stream) {
     if (encode_tmap(&tdw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.dw, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) != 0)
       return -1;
   }
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(&configured)) {
     TEDM_CUDA(cudaFuncSetAttribute(conv_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
-    configured = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * p.items * splits);
@@ -530,10 +529,9 @@ int conv_wgrad_launch(const ConvWgradArgs& a, cudaStream_t stream) {
     if (encode_tmap(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) != 0)
       return -1;
   }
-  static bool configured = false;
-  if (!configured) {
+  static unsigned long long configured = 0;
+  if (first_use_on_device(&configured)) {
     TEDM_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    configured = true;
   }
   conv_wgrad_kernel<<<p.items * splits, kThreads, kSmemBytes, stream>>>(tg, tx, p);
   TEDM_LAUNCH_CHECK();

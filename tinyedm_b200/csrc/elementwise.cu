@@ -671,7 +671,10 @@ int channel_dot(const ChannelDotArgs& a, cudaStream_t stream) {
   TEDM_CHECK(a.C % 8 == 0 && a.C / 8 <= 256 && a.C > 0 && a.CA % 8 == 0 && a.a_off % 8 == 0, "channel_dot: unsupported C=%d", a.C);
   const int nvec = a.C / 8;
   const int rows = 256 / nvec;
-  dim3 grid(pick_chunks(a.B, a.HW, rows), a.B);
+  // The forward use (spatial mean of the skip tensor, Bm == null) runs ONE CTA per image: a single, fixed-order reduction
+  // per (b, c) keeps eval-mode inference bit-reproducible (several CTAs per image would combine through fp32 atomics in
+  // arrival order, and 63 network evaluations amplify a 1e-7 difference to 1e-3). The backward use keeps the split.
+  dim3 grid(a.Bm == nullptr ? 1 : pick_chunks(a.B, a.HW, rows), a.B);
   size_t smem = (size_t)rows * a.C * sizeof(float);
   channel_dot_kernel<<<grid, 256, smem, stream>>>(a);
   TEDM_LAUNCH_CHECK();

@@ -41,6 +41,17 @@ int num_sms() {
   return n;
 }
 
+bool first_use_on_device(unsigned long long* device_mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  static std::mutex mu;
+  std::lock_guard<std::mutex> g(mu);
+  if (*device_mask & bit) return false;
+  *device_mask |= bit;
+  return true;
+}
+
 bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {
