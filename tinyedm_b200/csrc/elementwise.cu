@@ -514,13 +514,19 @@ __global__ void __launch_bounds__(256, 4)
 channel_dot_kernel(const ChannelDotArgs a) {
   pdl_trigger();   // a following tcgen05 kernel may run its prologue during this kernel's last wave
   extern __shared__ float sred[];
-  const int nvec = a.C / 8;
+  // Two decompositions: (a) pixel chunks (gridDim.x chunks of the image, all channels per CTA, partial sums combined with
+  // atomics) and (b) channel groups (a.group_c > 0: gridDim.x groups of group_c channels, the whole image per CTA: every
+  // (b, c) is reduced by exactly one CTA in a fixed order -> bit-reproducible).
+  const bool by_channel = a.group_c > 0;
+  const int c_cta = by_channel ? a.group_c : a.C;          // channels handled by this CTA
+  const int c_base = by_channel ? blockIdx.x * a.group_c : 0;
+  const int nvec = c_cta / 8;
   const int rows = blockDim.x / nvec;
   const int v = threadIdx.x % nvec;
   const int rr = threadIdx.x / nvec;
   const int b = blockIdx.y;
-  const int chunk = (a.HW + gridDim.x - 1) / gridDim.x;
-  const int p_begin = blockIdx.x * chunk;
+  const int chunk = by_channel ? a.HW : (a.HW + gridDim.x - 1) / gridDim.x;
+  const int p_begin = by_channel ? 0 : blockIdx.x * chunk;
   int p_end = p_begin + chunk;
   if (p_end > a.HW) p_end = a.HW;
   float acc[8];
@@ -535,8 +541,8 @@ channel_dot_kernel(const ChannelDotArgs a) {
         const int pp = p + u * rows;
         if (pp < p_end) {
           const long long row = (long long)b * a.HW + pp;
-          xr[u] = load_raw(a.A + row * a.CA + a.a_off + v * 8);
-          if (a.Bm != nullptr) yr[u] = load_raw(a.Bm + row * a.C + v * 8);
+          xr[u] = load_raw(a.A + row * a.CA + a.a_off + c_base + v * 8);
+          if (a.Bm != nullptr) yr[u] = load_raw(a.Bm + row * a.C + c_base + v * 8);
         }
       }
 #pragma unroll
@@ -555,16 +561,41 @@ channel_dot_kernel(const ChannelDotArgs a) {
       }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sred[rr * a.C + v * 8 + i] = acc[i];
+    for (int i = 0; i < 8; ++i) sred[rr * c_cta + v * 8 + i] = acc[i];
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+  for (int c = threadIdx.x; c < c_cta; c += blockDim.x) {
     float t = 0.f;
-    for (int r2 = 0; r2 < rows; ++r2) t += sred[r2 * a.C + c];
-    atomicAdd(a.out + (long long)b * a.C + c, t * a.scale);
+    for (int r2 = 0; r2 < rows; ++r2) t += sred[r2 * c_cta + c];
+    if (by_channel) a.out[(long long)b * a.C + c_base + c] += t * a.scale;   // sole writer of this element
+    else atomicAdd(a.out + (long long)b * a.C + c, t * a.scale);
   }
 }
 
+
+// a = mp_silu(in), nothing else (decoder blocks without skip / resample, networks.py:316): a flat stream of 16-byte
+// vectors, 4 in flight per thread; the generic warp-per-pixel kernel spends more instructions on bookkeeping than on data
+// for this case (54 % of HBM peak).
+__global__ void __launch_bounds__(256, 4)
+silu_flat_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, long long nvec) {
+  pdl_trigger();
+  const long long stride = (long long)gridDim.x * 256;
+  for (long long i0 = (long long)blockIdx.x * 256 + threadIdx.x; i0 < nvec; i0 += 4 * stride) {
+    uint4 r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u * stride < nvec) r[u] = load_raw(in + (i0 + u * stride) * 8);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + u * stride < nvec) {
+        Vec8 x = unpack8(r[u]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x.v[i] = mp_silu_f(x.v[i]);
+        store8(out + (i0 + u * stride) * 8, x);
+      }
+    }
+  }
+}
 
 int grid_for_warps(long long nwarps_needed, int warps_per_block) {
   long long blocks = (nwarps_needed + warps_per_block - 1) / warps_per_block;
@@ -586,6 +617,14 @@ int block_prep_forward(const PrepArgs& a, cudaStream_t stream) {
   const long long npix = (long long)a.B * H * W;
   if (npix == 0) return 0;
   TEDM_CHECK(npix < (1LL << 31) / 8, "block_prep: too many pixels");
+  if (a.resample == 0 && !a.pixelnorm && a.C2 == 0 && a.x_out == nullptr && a.a_out != nullptr) {
+    const long long nvec = npix * (C / 8);
+    long long blocks = (nvec + 1023) / 1024;
+    if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+    silu_flat_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.in, a.a_out, nvec);
+    TEDM_LAUNCH_CHECK();
+    return 0;
+  }
   const int nv = (C / 8 + 31) / 32;
   switch (nv) {
 #define TEDM_PREP_FWD(NV, PU)                                                                                         \
@@ -671,12 +710,16 @@ int channel_dot(const ChannelDotArgs& a, cudaStream_t stream) {
   TEDM_CHECK(a.C % 8 == 0 && a.C / 8 <= 256 && a.C > 0 && a.CA % 8 == 0 && a.a_off % 8 == 0, "channel_dot: unsupported C=%d", a.C);
   const int nvec = a.C / 8;
   const int rows = 256 / nvec;
-  // The forward use (spatial mean of the skip tensor, Bm == null) runs ONE CTA per image: a single, fixed-order reduction
-  // per (b, c) keeps eval-mode inference bit-reproducible (several CTAs per image would combine through fp32 atomics in
-  // arrival order, and 63 network evaluations amplify a 1e-7 difference to 1e-3). The backward use keeps the split.
-  dim3 grid(a.Bm == nullptr ? 1 : pick_chunks(a.B, a.HW, rows), a.B);
-  size_t smem = (size_t)rows * a.C * sizeof(float);
-  channel_dot_kernel<<<grid, 256, smem, stream>>>(a);
+  // The forward use (spatial mean of the skip tensor, Bm == null) splits the CHANNELS over CTAs (64 per CTA) instead of the
+  // pixels: every (b, c) is then reduced by exactly one CTA in a fixed order, which keeps eval-mode inference
+  // bit-reproducible (pixel chunks combine through fp32 atomics in arrival order, and 63 network evaluations amplify a
+  // 1e-7 difference to 1e-3). The backward use keeps the pixel split.
+  ChannelDotArgs k = a;
+  k.group_c = (a.Bm == nullptr && a.C % 64 == 0) ? 64 : 0;
+  dim3 grid(k.group_c > 0 ? a.C / 64 : (a.Bm == nullptr ? 1 : pick_chunks(a.B, a.HW, rows)), a.B);
+  const int rows_cta = k.group_c > 0 ? 256 / (k.group_c / 8) : rows;
+  size_t smem = (size_t)rows_cta * (k.group_c > 0 ? k.group_c : a.C) * sizeof(float);
+  channel_dot_kernel<<<grid, 256, smem, stream>>>(k);
   TEDM_LAUNCH_CHECK();
   return 0;
 }

@@ -132,6 +132,7 @@ struct ChannelDotArgs {
   float* out;               // (B,C) accumulated atomically (zero it first)
   int B, HW, C, CA, a_off;
   float scale;
+  int group_c;              // set by the launcher: > 0 = one CTA per group of this many channels (deterministic mode)
 };
 int channel_dot(const ChannelDotArgs& a, cudaStream_t stream);
 
