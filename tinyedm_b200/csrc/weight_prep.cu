@@ -73,7 +73,9 @@ __device__ __forceinline__ int find_group_tensor(const WeightDesc* table, int n,
 
 constexpr int kGroupRows = 16;     // prepared rows per CTA: 16 bf16 = one 32-byte sector of the data-gradient layout
 constexpr int kFwdThreads = 256;
-constexpr int kTileElems = 576;    // fan-in elements staged per row and pass (64 input channels of a 3x3 filter)
+// fan-in elements staged per row and pass (64 input channels of a 3x3 filter). 288 (18.5 KB tiles, 8 CTAs per SM, the whole
+// CIFAR net in one wave) was measured slower: 267 us vs 210 us — the extra barrier round trips cost more than the tail.
+constexpr int kTileElems = 576;
 constexpr int kTileStride = kTileElems + 1;   // odd stride: conflict-free column reads
 
 // One CTA = 16 consecutive PREPARED rows of one tensor.
@@ -232,18 +234,29 @@ weight_prep_bwd_kernel(const WeightDesc* __restrict__ table, int n_tensors) {
     grow[tap * (cin + 1) + ci] = g[k];
   }
   __syncthreads();
+  // j = ci * taps + tap walks the parameter row; (ci, tap) advance incrementally (no div/mod per element)
+  const int step_ci = kThreads / taps, step_tap = kThreads - step_ci * taps;
+  const int ci0 = threadIdx.x / taps, tap0 = threadIdx.x - ci0 * taps;
   float dot = 0.f;
-  for (int j = threadIdx.x; j < fan_in; j += kThreads) {
-    const int ci = j / taps, tap = j - ci * taps;
-    dot += w[j] * grow[tap * (cin + 1) + ci];
+  {
+    int ci = ci0, tap = tap0;
+    for (int j = threadIdx.x; j < fan_in; j += kThreads) {
+      dot += w[j] * grow[tap * (cin + 1) + ci];
+      ci += step_ci; tap += step_tap;
+      if (tap >= taps) { tap -= taps; ++ci; }
+    }
   }
   dot = block_sum(dot, red);
   const float inv_s = stats[2 * row + 0];
   const float norm = stats[2 * row + 1];
   const float c2 = dot * inv_s * inv_s / fmaxf(norm, 1e-30f);
-  for (int j = threadIdx.x; j < fan_in; j += kThreads) {
-    const int ci = j / taps, tap = j - ci * taps;
-    out[j] = grow[tap * (cin + 1) + ci] * inv_s - w[j] * c2;
+  {
+    int ci = ci0, tap = tap0;
+    for (int j = threadIdx.x; j < fan_in; j += kThreads) {
+      out[j] = grow[tap * (cin + 1) + ci] * inv_s - w[j] * c2;
+      ci += step_ci; tap += step_tap;
+      if (tap >= taps) { tap -= taps; ++ci; }
+    }
   }
 }
 
