@@ -584,7 +584,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-    if (elected) bulk_wait_all0();
+    if (elected) bulk_wait_read0();   // shared memory must outlive the stores' reads; their global writes complete with the grid
   }
 
   tc_fence_before();

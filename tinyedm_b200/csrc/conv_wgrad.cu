@@ -377,7 +377,7 @@ conv_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
           else tma_store_2d(&tmap_dw, buf, tap * p.Cin + ci0 + c * 32, co0);
         }
         bulk_commit();
-        bulk_wait_all0();
+        bulk_wait_read0();   // shared memory must outlive the reads; the global updates complete with the grid
       }
     }
   }
