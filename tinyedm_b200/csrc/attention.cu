@@ -256,6 +256,8 @@ template <int HD>
 __global__ void __launch_bounds__(kThreads)
 attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ y, float* __restrict__ lse, int B, int S,
                 int heads, float scale) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   constexpr int LD = HD + 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int Sp = (S + kBlk - 1) / kBlk * kBlk;
@@ -343,6 +345,8 @@ __global__ void __launch_bounds__(kThreads)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ y,
                    const __nv_bfloat16* __restrict__ g_y, const float* __restrict__ lse, float* __restrict__ delta,
                    __nv_bfloat16* __restrict__ g_qkv, int B, int S, int heads, float scale) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   constexpr int LD = HD + 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int Sp = (S + kBlk - 1) / kBlk * kBlk;
@@ -437,6 +441,8 @@ __global__ void __launch_bounds__(kThreads)
 attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ g_y,
                     const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ g_qkv,
                     int B, int S, int heads, float scale) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   constexpr int LD = HD + 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
   const int Sp = (S + kBlk - 1) / kBlk * kBlk;
@@ -545,7 +551,7 @@ int launch_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* y, float* lse, int B, in
   const size_t smem = smem_fwd(S, HD);
   if (set_smem(attn_fwd_kernel<HD>, smem) != 0) return -1;
   dim3 grid((S + kBlk - 1) / kBlk, B * heads);
-  attn_fwd_kernel<HD><<<grid, kThreads, smem, stream>>>(qkv, y, lse, B, S, heads, 1.0f / sqrtf((float)HD));
+  launch_pdl(attn_fwd_kernel<HD>, grid, kThreads, smem, stream, qkv, y, lse, B, S, heads, 1.0f / sqrtf((float)HD));
   TEDM_LAUNCH_CHECK();
   return 0;
 }
@@ -558,13 +564,13 @@ int launch_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* y, const __nv_bflo
   {
     const size_t smem = smem_dq(S, HD);
     if (set_smem(attn_bwd_dq_kernel<HD>, smem) != 0) return -1;
-    attn_bwd_dq_kernel<HD><<<grid, kThreads, smem, stream>>>(qkv, y, g_y, lse, delta, g_qkv, B, S, heads, scale);
+    launch_pdl(attn_bwd_dq_kernel<HD>, grid, kThreads, smem, stream, qkv, y, g_y, lse, delta, g_qkv, B, S, heads, scale);
     TEDM_LAUNCH_CHECK();
   }
   {
     const size_t smem = smem_dkv(S, HD);
     if (set_smem(attn_bwd_dkv_kernel<HD, QC>, smem) != 0) return -1;
-    attn_bwd_dkv_kernel<HD, QC><<<grid, kThreads, smem, stream>>>(qkv, g_y, lse, delta, g_qkv, B, S, heads, scale);
+    launch_pdl(attn_bwd_dkv_kernel<HD, QC>, grid, kThreads, smem, stream, qkv, g_y, lse, delta, g_qkv, B, S, heads, scale);
     TEDM_LAUNCH_CHECK();
   }
   return 0;

@@ -111,6 +111,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();   // the prologue above overlapped the previous kernel's tail; its results are needed from here on
 
   if (warp == 4) {
     if (lane == 0) {
@@ -393,6 +394,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();   // the prologue above overlapped the previous kernel's tail; its results are needed from here on
 
   float n_q = 1.f, dl = 0.f, ls2 = 0.f;
   if (warp == 8) {
@@ -588,6 +590,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();   // the prologue above overlapped the previous kernel's tail; its results are needed from here on
 
   float n_k = 1.f, n_v = 1.f;
   if (warp == 8) {
@@ -776,9 +779,9 @@ int launch_bwd_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* y, const __nv_b
   const int n_pairs = B * heads;
   const int grid = S == 256 ? n_pairs * 2 : (n_pairs + 1) / 2;
   const float scale = 1.0f / sqrtf((float)kHD);
-  attn_bwd_dq_tc_kernel<S><<<grid, kThreadsB, kDqSmem, stream>>>(t_tile, t_all, t_do_tile, y, lse, delta, g_qkv, n_pairs, heads, scale);
+  launch_pdl(attn_bwd_dq_tc_kernel<S>, grid, kThreadsB, kDqSmem, stream, t_tile, t_all, t_do_tile, y, lse, delta, g_qkv, n_pairs, heads, scale);
   TEDM_LAUNCH_CHECK();
-  attn_bwd_dkv_tc_kernel<S><<<grid, kThreadsB, kKvSmem, stream>>>(t_tile, t_all, t_do_all, lse, delta, g_qkv, n_pairs, heads, scale);
+  launch_pdl(attn_bwd_dkv_tc_kernel<S>, grid, kThreadsB, kKvSmem, stream, t_tile, t_all, t_do_all, lse, delta, g_qkv, n_pairs, heads, scale);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
@@ -799,7 +802,7 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* y, float* lse, int B, int
   }
   const int n_pairs = B * heads;
   const int grid = S == 256 ? n_pairs * 2 : (n_pairs + 1) / 2;
-  attn_fwd_tc_kernel<S><<<grid, kThreadsA, kSmemBytesA, stream>>>(tq, tkv, y, lse, n_pairs, heads, 1.0f / sqrtf((float)kHD));
+  launch_pdl(attn_fwd_tc_kernel<S>, grid, kThreadsA, kSmemBytesA, stream, tq, tkv, y, lse, n_pairs, heads, 1.0f / sqrtf((float)kHD));
   TEDM_LAUNCH_CHECK();
   return 0;
 }

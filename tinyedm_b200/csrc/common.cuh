@@ -3,6 +3,7 @@
 // Everything here is hand-written PTX glue for Blackwell (mbarrier, TMA, tcgen05/TMEM)
 // plus small bf16/vector utilities used by the bandwidth-bound kernels.
 #pragma once
+#include <utility>
 
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -42,6 +43,24 @@ bool pdl_enabled();
 // shared-memory limit are per device, and a process may drive more than one.
 bool first_use_on_device(unsigned long long* device_mask);   // TEDM_PDL=0 disables programmatic dependent launches (A/B switch)
 const char* last_error();
+
+// Launch with the programmatic-stream-serialization attribute (unless TEDM_PDL=0): the grid may be scheduled while the
+// previous kernel in the stream drains. EVERY kernel launched this way calls pdl_wait() before its first global access.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // Encodes a tiled TMA descriptor through the driver entry point (resolved at run time so the
 // library carries no link-time dependency on libcuda).

@@ -96,6 +96,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                      // programmatic dependent launch: the prologue above overlaps the previous kernel's tail
+  if (threadIdx.x == 0) pdl_trigger();
 
   if (warp == 0) {
     const bool leader_lane = elect_one();   // warp-uniform loop, one elected lane issues
@@ -533,7 +535,7 @@ int conv_wgrad_launch(const ConvWgradArgs& a, cudaStream_t stream) {
   if (first_use_on_device(&configured)) {
     TEDM_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   }
-  conv_wgrad_kernel<<<p.items * splits, kThreads, kSmemBytes, stream>>>(tg, tx, p);
+  launch_pdl(conv_wgrad_kernel, p.items * splits, kThreads, kSmemBytes, stream, tg, tx, p);
   TEDM_LAUNCH_CHECK();
   return 0;
 }

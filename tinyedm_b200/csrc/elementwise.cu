@@ -59,7 +59,8 @@ __device__ __forceinline__ Vec8 load8f(const float* p) {
 template <int NV, int PU, bool kPool>
 __global__ void __launch_bounds__(256, (NV * PU <= 4) ? 4 : 2)
 block_prep_fwd_kernel(const PrepArgs a) {
-  pdl_trigger();   // a following tcgen05 kernel may run its prologue during this kernel's last wave
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   const int H = a.resample == 1 ? a.Hin / 2 : (a.resample == 2 ? a.Hin * 2 : a.Hin);
   const int W = a.resample == 1 ? a.Win / 2 : (a.resample == 2 ? a.Win * 2 : a.Win);
   const int C = a.C1 + a.C2;
@@ -251,7 +252,8 @@ __device__ __forceinline__ void prep_bwd_store(const PrepBwdArgs& a, int b, long
 template <int NV>
 __global__ void __launch_bounds__(256)
 block_prep_bwd_kernel(const PrepBwdArgs a) {
-  pdl_trigger();   // a following tcgen05 kernel may run its prologue during this kernel's last wave
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   const int H = a.resample == 1 ? a.Hin / 2 : (a.resample == 2 ? a.Hin * 2 : a.Hin);
   const int W = a.resample == 1 ? a.Win / 2 : (a.resample == 2 ? a.Win * 2 : a.Win);
   const int C = a.C1 + a.C2;
@@ -319,7 +321,8 @@ block_prep_bwd_kernel(const PrepBwdArgs a) {
 template <int NV, int PU, bool kUp>
 __global__ void __launch_bounds__(256, (NV * PU <= 4 && !kUp) ? 3 : 2)
 block_prep_bwd_light_kernel(const PrepBwdArgs a) {
-  pdl_trigger();   // a following tcgen05 kernel may run its prologue during this kernel's last wave
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   const int C = a.C1 + a.C2;
   const int nvec = C / 8;
   const int lane = threadIdx.x & 31;
@@ -455,6 +458,8 @@ block_prep_bwd_light_kernel(const PrepBwdArgs a) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 modsilu_bwd_kernel(const ModSiluBwdArgs a) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   extern __shared__ float sred[];  // [rows][C]
   const int nvec = a.C / 8;
   const int rows = blockDim.x / nvec;  // pixel rows processed in parallel
@@ -512,7 +517,8 @@ modsilu_bwd_kernel(const ModSiluBwdArgs a) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 4)
 channel_dot_kernel(const ChannelDotArgs a) {
-  pdl_trigger();   // a following tcgen05 kernel may run its prologue during this kernel's last wave
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   extern __shared__ float sred[];
   // Two decompositions: (a) pixel chunks (gridDim.x chunks of the image, all channels per CTA, partial sums combined with
   // atomics) and (b) channel groups (a.group_c > 0: gridDim.x groups of group_c channels, the whole image per CTA: every
@@ -578,7 +584,8 @@ channel_dot_kernel(const ChannelDotArgs a) {
 // for this case (54 % of HBM peak).
 __global__ void __launch_bounds__(256, 4)
 silu_flat_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, long long nvec) {
-  pdl_trigger();
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   const long long stride = (long long)gridDim.x * 256;
   for (long long i0 = (long long)blockIdx.x * 256 + threadIdx.x; i0 < nvec; i0 += 4 * stride) {
     uint4 r[4];
@@ -621,7 +628,7 @@ int block_prep_forward(const PrepArgs& a, cudaStream_t stream) {
     const long long nvec = npix * (C / 8);
     long long blocks = (nvec + 1023) / 1024;
     if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
-    silu_flat_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a.in, a.a_out, nvec);
+    launch_pdl(silu_flat_kernel, (unsigned)blocks, 256, 0, stream, a.in, a.a_out, nvec);
     TEDM_LAUNCH_CHECK();
     return 0;
   }
@@ -630,8 +637,8 @@ int block_prep_forward(const PrepArgs& a, cudaStream_t stream) {
 #define TEDM_PREP_FWD(NV, PU)                                                                                         \
   do {                                                                                                                \
     const int grid = grid_for_warps((npix + PU - 1) / PU, 8);                                                         \
-    if (a.resample == 1) block_prep_fwd_kernel<NV, 1, true><<<grid_for_warps(npix, 8), 256, 0, stream>>>(a);          \
-    else block_prep_fwd_kernel<NV, PU, false><<<grid, 256, 0, stream>>>(a);                                           \
+    if (a.resample == 1) launch_pdl(block_prep_fwd_kernel<NV, 1, true>, grid_for_warps(npix, 8), 256, 0, stream, a);          \
+    else launch_pdl(block_prep_fwd_kernel<NV, PU, false>, grid, 256, 0, stream, a);                                           \
   } while (0)
     case 1: TEDM_PREP_FWD(1, 4); break;
     case 2: TEDM_PREP_FWD(2, 2); break;
@@ -659,8 +666,8 @@ int block_prep_backward(const PrepBwdArgs& a, cudaStream_t stream) {
     switch (nvl) {
 #define TEDM_PREP_BWD(NV, PU)                                                                                         \
   do {                                                                                                                \
-    if (a.resample == 2) block_prep_bwd_light_kernel<NV, 1, true><<<grid_for_warps(ndst, 8), 256, 0, stream>>>(a);    \
-    else block_prep_bwd_light_kernel<NV, PU, false><<<grid_for_warps((ndst + PU - 1) / PU, 8), 256, 0, stream>>>(a);  \
+    if (a.resample == 2) launch_pdl(block_prep_bwd_light_kernel<NV, 1, true>, grid_for_warps(ndst, 8), 256, 0, stream, a);    \
+    else launch_pdl(block_prep_bwd_light_kernel<NV, PU, false>, grid_for_warps((ndst + PU - 1) / PU, 8), 256, 0, stream, a);  \
   } while (0)
       case 1: TEDM_PREP_BWD(1, 4); break;
       case 2: TEDM_PREP_BWD(2, 2); break;
@@ -675,11 +682,11 @@ int block_prep_backward(const PrepBwdArgs& a, cudaStream_t stream) {
   const int nv = (C / 8 + 31) / 32;
   const int grid = grid_for_warps(npix, 8);
   switch (nv) {
-    case 1: block_prep_bwd_kernel<1><<<grid, 256, 0, stream>>>(a); break;
-    case 2: block_prep_bwd_kernel<2><<<grid, 256, 0, stream>>>(a); break;
-    case 3: block_prep_bwd_kernel<3><<<grid, 256, 0, stream>>>(a); break;
-    case 4: block_prep_bwd_kernel<4><<<grid, 256, 0, stream>>>(a); break;
-    default: block_prep_bwd_kernel<6><<<grid, 256, 0, stream>>>(a); break;
+    case 1: launch_pdl(block_prep_bwd_kernel<1>, grid, 256, 0, stream, a); break;
+    case 2: launch_pdl(block_prep_bwd_kernel<2>, grid, 256, 0, stream, a); break;
+    case 3: launch_pdl(block_prep_bwd_kernel<3>, grid, 256, 0, stream, a); break;
+    case 4: launch_pdl(block_prep_bwd_kernel<4>, grid, 256, 0, stream, a); break;
+    default: launch_pdl(block_prep_bwd_kernel<6>, grid, 256, 0, stream, a); break;
   }
   TEDM_LAUNCH_CHECK();
   return 0;
@@ -701,7 +708,7 @@ int modsilu_backward(const ModSiluBwdArgs& a, cudaStream_t stream) {
   TEDM_CHECK(rows >= 1, "modsilu_bwd: C too large");
   dim3 grid(pick_chunks(a.B, a.HW, rows), a.B);
   size_t smem = (size_t)rows * a.C * sizeof(float);
-  modsilu_bwd_kernel<<<grid, 256, smem, stream>>>(a);
+  launch_pdl(modsilu_bwd_kernel, grid, 256, smem, stream, a);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
@@ -719,7 +726,7 @@ int channel_dot(const ChannelDotArgs& a, cudaStream_t stream) {
   dim3 grid(k.group_c > 0 ? a.C / 64 : (a.Bm == nullptr ? 1 : pick_chunks(a.B, a.HW, rows)), a.B);
   const int rows_cta = k.group_c > 0 ? 256 / (k.group_c / 8) : rows;
   size_t smem = (size_t)rows_cta * (k.group_c > 0 ? k.group_c : a.C) * sizeof(float);
-  channel_dot_kernel<<<grid, 256, smem, stream>>>(k);
+  launch_pdl(channel_dot_kernel, grid, 256, smem, stream, k);
   TEDM_LAUNCH_CHECK();
   return 0;
 }

@@ -33,6 +33,8 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 __global__ void __launch_bounds__(kThreads)
 adam_ema_kernel(const tedm_adam_desc* __restrict__ table, const int2* __restrict__ chunks, float lr, float step,
                 const float* __restrict__ hyper, float beta1, float beta2, float eps, float gamma) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   if (hyper != nullptr) { lr = hyper[0]; step = hyper[1]; }
   AdamScalars s;
   s.beta1 = beta1; s.beta2 = beta2; s.eps = eps;
@@ -89,7 +91,7 @@ int adam_ema_step(const tedm_adam_desc* table, const int32_t* chunks, int n_chun
                   float beta1, float beta2, float eps, float gamma, cudaStream_t stream) {
   if (n_chunks <= 0) return 0;
   TEDM_CHECK(hyper != nullptr || step >= 1.0f, "adam: step counts from 1");
-  adam_ema_kernel<<<n_chunks, kThreads, 0, stream>>>(table, reinterpret_cast<const int2*>(chunks), lr, step, hyper, beta1,
+  launch_pdl(adam_ema_kernel, n_chunks, kThreads, 0, stream, table, reinterpret_cast<const int2*>(chunks), lr, step, hyper, beta1,
                                                     beta2, eps, gamma);
   TEDM_LAUNCH_CHECK();
   return 0;

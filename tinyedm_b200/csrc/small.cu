@@ -26,8 +26,10 @@ constexpr int TS = 64, TK = 16;
 __global__ void __launch_bounds__(256)
 sgemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ C, int M, int N, int K,
              int lda, int ldb, int ldc, int transA, int transB, float alpha, float beta, int k_chunk) {
-  __shared__ float As[TK][TS + 1];
-  __shared__ float Bs[TK][TS + 1];
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
+  __shared__ __align__(16) float As[TK][TS + 4];   // +4: rows stay 16-byte aligned for the float4 reads below
+  __shared__ __align__(16) float Bs[TK][TS + 4];
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   const int m0 = blockIdx.y * TS, n0 = blockIdx.x * TS;
   // split-K: blockIdx.z owns K range [k_begin, k_end); partial results are combined with atomics into a zeroed C
@@ -55,11 +57,9 @@ sgemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* _
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < TK; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+      const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -85,6 +85,8 @@ sgemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* _
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 embedding_fwd_kernel(const EmbeddingArgs a) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   extern __shared__ float four_s[];  // [F]
   const int b = blockIdx.x;
   const float sigma = a.sigma[a.sigma_stride * b];
@@ -114,6 +116,8 @@ embedding_fwd_kernel(const EmbeddingArgs a) {
 // g_pre = g_emb * mp_silu'(pre); g_sig = g_pre * (1-t)/c (or g_pre); scatter class-weight gradient
 __global__ void __launch_bounds__(256)
 embedding_bwd_kernel(const EmbeddingBwdArgs a) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   const int b = blockIdx.x;
   const float t = a.add_factor;
   const float inv_c = rsqrtf((1.f - t) * (1.f - t) + t * t);
@@ -134,6 +138,8 @@ embedding_bwd_kernel(const EmbeddingBwdArgs a) {
 // ------------------------------------------------------------------------------------------------
 __global__ void mod_finish_fwd_kernel(const float* __restrict__ lin, const float* const* __restrict__ gains,
                                       const int* __restrict__ col_block, float* __restrict__ m, int B, int N) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * N) return;
   const int col = (int)(i % N);
@@ -146,6 +152,8 @@ __global__ void __launch_bounds__(256)
 mod_finish_bwd_kernel(const float* __restrict__ lin, const float* __restrict__ dm, const float* const* __restrict__ gains,
                       const int* __restrict__ blk_start, float* __restrict__ d_lin, float* __restrict__ d_gain, int B,
                       int N) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   __shared__ float red[8];
   const int blk = blockIdx.x;
   const int c0 = blk_start[blk], c1 = blk_start[blk + 1];
@@ -176,6 +184,8 @@ mod_finish_bwd_kernel(const float* __restrict__ lin, const float* __restrict__ d
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 scalelong_fwd_kernel(const ScaleLongArgs a) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   extern __shared__ float sm[];  // aug[C+1], h[R]
   float* aug = sm;
   float* h = sm + a.C + 1;
@@ -214,6 +224,8 @@ scalelong_fwd_kernel(const ScaleLongArgs a) {
 
 __global__ void __launch_bounds__(256)
 scalelong_bwd_kernel(const ScaleLongBwdArgs a) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   extern __shared__ float sm[];  // dp2[C], dhp[R]
   float* dp2 = sm;
   float* dhp = sm + a.C;
@@ -250,6 +262,8 @@ scalelong_bwd_kernel(const ScaleLongBwdArgs a) {
 __global__ void __launch_bounds__(256)
 scalelong_wgrad_kernel(const float* __restrict__ d_pre2, const float* __restrict__ h, const float* __restrict__ d_hpre,
                        const float* __restrict__ aug, float* __restrict__ dw2, float* __restrict__ dw1, int B, int C, int R) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   const int n2 = C * R, n1 = R * (C + 1);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n1 + n2) return;
@@ -274,6 +288,8 @@ scalelong_wgrad_kernel(const float* __restrict__ d_pre2, const float* __restrict
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 uncertainty_fwd_kernel(const UncertaintyArgs a) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   extern __shared__ float sm[];  // aug[F+1], h[F]
   float* aug = sm;
   float* h = sm + a.F + 1;
@@ -312,6 +328,8 @@ uncertainty_fwd_kernel(const UncertaintyArgs a) {
 // g_uraw[b] = g_u[b]*gain ; g_hpre[b,j] = g_uraw*w2[j]*silu'(h_pre)
 __global__ void __launch_bounds__(256)
 uncertainty_bwd_kernel(const UncertaintyBwdArgs a) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   const int b = blockIdx.x;
   const float gr = a.g_u[b] * *a.gain;
   if (threadIdx.x == 0) a.g_uraw[b] = gr;
@@ -325,6 +343,8 @@ uncertainty_bwd_kernel(const UncertaintyBwdArgs a) {
 __global__ void __launch_bounds__(256)
 conv_in_im2col_kernel(const float* __restrict__ noisy, const float* __restrict__ sigma, int sigma_stride,
                       float sigma_data, __nv_bfloat16* __restrict__ out, int B, int Ci, int H, int W) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (pixel, group of 8 k)
   const long long total = (long long)B * H * W * 8;
   if (idx >= total) return;
@@ -358,7 +378,9 @@ conv_in_im2col_kernel(const float* __restrict__ noisy, const float* __restrict__
 constexpr int kMaxCo = 4;
 
 __global__ void __launch_bounds__(256)
-conv_out_fwd_kernel(const ConvOutArgs a) {
+conv_out_fwd_generic_kernel(const ConvOutArgs a) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long npix = (long long)a.B * a.HW;
@@ -391,7 +413,9 @@ conv_out_fwd_kernel(const ConvOutArgs a) {
 }
 
 __global__ void __launch_bounds__(256)
-conv_out_bwd_kernel(const ConvOutBwdArgs a) {
+conv_out_bwd_generic_kernel(const ConvOutBwdArgs a) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   // Each lane owns groups of 8 consecutive channels (one 16-byte access per pixel); a warp walks pixels.
   //   g_f = g_D * c_out(sigma_b);  d gain_out += g_f * f_raw;  g_x = gain_out * sum_o g_f[o] w[o];  dW[o] += gain_out g_f[o] x
   extern __shared__ float sm[];  // [warps][Co*C] partial dW
@@ -494,6 +518,196 @@ conv_out_bwd_kernel(const ConvOutBwdArgs a) {
   if (lane == 0 && dgain != 0.f) atomicAdd(a.g_gain_out, dgain);
 }
 
+
+// ---- C <= 256 (every shipped config: 256 / 128 / 192 channels into conv_out): a lane owns 8 consecutive channels of a
+// pixel (one 16-byte access), w_hat lives in registers, 8 pixels are in flight per warp and 2 CTAs are resident per SM.
+// Sum over lanes of v[j] for every j at once: after the call lane l holds the total of v[l % N] (N a power of two <= 32).
+// N-1 exchanges for the transposing part instead of 5 N for N separate butterflies.
+template <int N>
+__device__ __forceinline__ float warp_sum_transposed(float (&v)[N], int lane) {
+#pragma unroll
+  for (int off = N / 2; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      const float send = hi ? v[j] : v[j + off];
+      const float keep = hi ? v[j + off] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  float t = v[0];
+#pragma unroll
+  for (int off = N; off < 32; off <<= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+  return t;
+}
+
+template <int CO>
+__global__ void __launch_bounds__(256, 2)
+conv_out_fwd_kernel(const ConvOutArgs a) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
+  constexpr int PU = 8;                                   // pixels in flight per warp
+  constexpr int NV = CO == 1 ? 8 : (CO == 2 ? 16 : 32);   // reduction slots: index = o * PU + u
+  const int lane = threadIdx.x & 31;
+  const long long npix = (long long)a.B * a.HW;
+  const long long ngrp = (npix + PU - 1) / PU;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const bool on = lane * 8 < a.C;
+  float wv[CO][8];
+#pragma unroll
+  for (int o = 0; o < CO; ++o) {
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (on) u = *reinterpret_cast<const uint4*>(a.w + (size_t)o * a.C + lane * 8);
+    const float2 p0 = unpack_bf16(u.x), p1 = unpack_bf16(u.y), p2 = unpack_bf16(u.z), p3 = unpack_bf16(u.w);
+    wv[o][0] = p0.x; wv[o][1] = p0.y; wv[o][2] = p1.x; wv[o][3] = p1.y;
+    wv[o][4] = p2.x; wv[o][5] = p2.y; wv[o][6] = p3.x; wv[o][7] = p3.y;
+  }
+  const float gain_out = *a.gain_out;
+  const float sd = a.sigma_data;
+  for (long long g = warp0; g < ngrp; g += nwarps) {
+    const long long pix0 = g * PU;
+    uint4 xr[PU];
+#pragma unroll
+    for (int u = 0; u < PU; ++u) {
+      xr[u] = make_uint4(0, 0, 0, 0);
+      if (on && pix0 + u < npix) xr[u] = *reinterpret_cast<const uint4*>(a.x + (pix0 + u) * a.C + lane * 8);
+    }
+    float v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = 0.f;
+#pragma unroll
+    for (int u = 0; u < PU; ++u) {
+      const float2 p0 = unpack_bf16(xr[u].x), p1 = unpack_bf16(xr[u].y), p2 = unpack_bf16(xr[u].z), p3 = unpack_bf16(xr[u].w);
+      const float xv[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+#pragma unroll
+      for (int o = 0; o < CO; ++o) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t = fmaf(xv[i], wv[o][i], t);
+        v[o * PU + u] = t;
+      }
+    }
+    const float f = warp_sum_transposed<NV>(v, lane);
+    const int slot = lane % NV;
+    const int o = slot / PU, u = slot % PU;
+    const long long pix = pix0 + u;
+    if (lane < NV && o < CO && pix < npix) {
+      const int b = (int)(pix / a.HW);
+      const int p = (int)(pix - (long long)b * a.HW);
+      const float s = a.sigma[b * a.sigma_stride];
+      const float c_skip = sd * sd / (s * s + sd * sd);
+      const float c_out = s * sd * rsqrtf(s * s + sd * sd);
+      const size_t oi = ((size_t)b * CO + o) * a.HW + p;
+      if (a.f_raw != nullptr) a.f_raw[oi] = f;
+      a.D[oi] = f * gain_out * c_out + a.noisy[oi] * c_skip;
+    }
+  }
+}
+
+template <int CO>
+__global__ void __launch_bounds__(256, 2)
+conv_out_bwd_kernel(const ConvOutBwdArgs a) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
+  //   g_f = g_D * c_out(sigma_b);  d gain_out += g_f * f_raw;  g_x = gain_out * sum_o g_f[o] w[o];  dW[o] += gain_out g_f[o] x
+  // A warp takes 32 consecutive pixels: lane l prepares g_f of pixel l (coalesced reads of g_D / f_raw), then the warp
+  // walks the 32 pixels PU at a time with the per-pixel g_f broadcast by shuffles.
+  constexpr int PU = CO == 4 ? 4 : 8;
+  extern __shared__ float sm[];  // [warps][CO*C] partial dW
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long npix = (long long)a.B * a.HW;
+  const long long nchunk = (npix + 31) / 32;
+  const long long warp0 = (long long)blockIdx.x * nw + wib;
+  const long long nwarps = (long long)gridDim.x * nw;
+  const bool on = lane * 8 < a.C;
+  const float gain_out = *a.gain_out;
+  const float sd = a.sigma_data;
+  uint4 wq[CO];          // w_hat stays packed (bf16 pairs) to leave registers for the pixels in flight
+  float dw[CO][8];
+#pragma unroll
+  for (int o = 0; o < CO; ++o) {
+    wq[o] = make_uint4(0, 0, 0, 0);
+    if (on) wq[o] = *reinterpret_cast<const uint4*>(a.w + (size_t)o * a.C + lane * 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dw[o][i] = 0.f;
+  }
+  float dgain = 0.f;
+  for (long long ch = warp0; ch < nchunk; ch += nwarps) {
+    const long long cpix0 = ch * 32;
+    float gf[CO];
+#pragma unroll
+    for (int o = 0; o < CO; ++o) gf[o] = 0.f;
+    {
+      const long long pix = cpix0 + lane;
+      if (pix < npix) {
+        const int b = (int)(pix / a.HW);
+        const int p = (int)(pix - (long long)b * a.HW);
+        const float s = a.sigma[b * a.sigma_stride];
+        const float cs = s * sd * rsqrtf(s * s + sd * sd);
+#pragma unroll
+        for (int o = 0; o < CO; ++o) {
+          const size_t oi = ((size_t)b * CO + o) * a.HW + p;
+          const float g1 = a.g_D[oi] * cs;
+          dgain = fmaf(g1, a.f_raw[oi], dgain);
+          gf[o] = g1 * gain_out;
+        }
+      }
+    }
+#pragma unroll 1
+    for (int sub = 0; sub < 32; sub += PU) {
+      const long long pix0 = cpix0 + sub;
+      if (pix0 >= npix) break;
+      uint4 xr[PU];
+#pragma unroll
+      for (int u = 0; u < PU; ++u) {
+        xr[u] = make_uint4(0, 0, 0, 0);
+        if (on && pix0 + u < npix) xr[u] = *reinterpret_cast<const uint4*>(a.x + (pix0 + u) * a.C + lane * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < PU; ++u) {
+        float g[CO];
+#pragma unroll
+        for (int o = 0; o < CO; ++o) g[o] = __shfl_sync(0xffffffffu, gf[o], sub + u);
+        const float2 p0 = unpack_bf16(xr[u].x), p1 = unpack_bf16(xr[u].y), p2 = unpack_bf16(xr[u].z), p3 = unpack_bf16(xr[u].w);
+        const float xv[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+        float gx[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gx[i] = 0.f;
+#pragma unroll
+        for (int o = 0; o < CO; ++o) {
+          const float2 w0 = unpack_bf16(wq[o].x), w1 = unpack_bf16(wq[o].y), w2 = unpack_bf16(wq[o].z), w3 = unpack_bf16(wq[o].w);
+          const float wv[8] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y, w3.x, w3.y};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            gx[i] = fmaf(g[o], wv[i], gx[i]);
+            dw[o][i] = fmaf(g[o], xv[i], dw[o][i]);
+          }
+        }
+        if (on && pix0 + u < npix) {
+          uint4 o4;
+          o4.x = pack_bf16(gx[0], gx[1]); o4.y = pack_bf16(gx[2], gx[3]); o4.z = pack_bf16(gx[4], gx[5]); o4.w = pack_bf16(gx[6], gx[7]);
+          *reinterpret_cast<uint4*>(a.g_x + (pix0 + u) * a.C + lane * 8) = o4;
+        }
+      }
+    }
+  }
+  if (on) {
+#pragma unroll
+    for (int o = 0; o < CO; ++o)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sm[(size_t)wib * CO * a.C + (size_t)o * a.C + lane * 8 + i] = dw[o][i];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < CO * a.C; idx += blockDim.x) {
+    float t = 0.f;
+    for (int w2 = 0; w2 < nw; ++w2) t += sm[(size_t)w2 * CO * a.C + idx];
+    atomicAdd(a.g_w + idx, t);
+  }
+  dgain = warp_sum(dgain);
+  if (lane == 0 && dgain != 0.f) atomicAdd(a.g_gain_out, dgain);
+}
+
 // ------------------------------------------------------------------------------------------------
 // weighted MSE (+ uncertainty)
 // ------------------------------------------------------------------------------------------------
@@ -510,6 +724,8 @@ __global__ void __launch_bounds__(256)
 wmse_fwd_kernel(const float* __restrict__ D, const float* __restrict__ y, const float* __restrict__ sigma,
                 const float* __restrict__ u, const float* __restrict__ weight, float sigma_data, float* __restrict__ mse,
                 float* __restrict__ wsum, float* __restrict__ loss, int B, int n) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   __shared__ float red[8];
   const int b = blockIdx.x;
   const float* d = D + (size_t)b * n;
@@ -549,6 +765,8 @@ wmse_bwd_kernel(const float* __restrict__ D, const float* __restrict__ y, const 
                 const float* __restrict__ u, const float* __restrict__ weight, const float* __restrict__ mse,
                 const float* __restrict__ g_loss, float sigma_data, float* __restrict__ g_D, float* __restrict__ g_u,
                 float* __restrict__ g_weight, int B, int n) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   const int b = blockIdx.y;
   const float w = wmse_weight(weight, sigma, u, sigma_data, b);
   const float gl = *g_loss;
@@ -569,6 +787,8 @@ wmse_bwd_kernel(const float* __restrict__ D, const float* __restrict__ y, const 
 __global__ void heun_step_kernel(const float* __restrict__ x0, const float* __restrict__ x1, const float* __restrict__ D,
                                  const float* __restrict__ d_prev, float* __restrict__ x_out, float* __restrict__ d_out,
                                  const float* __restrict__ ts, int step, int mode, long long n) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float t0 = ts[step], t1 = ts[step + 1];
@@ -588,6 +808,8 @@ __global__ void heun_step_kernel(const float* __restrict__ x0, const float* __re
 __global__ void diffuse_kernel(const float* __restrict__ clean, const float* __restrict__ eps,
                                const float* __restrict__ noise, float P_mean, float P_std, float* __restrict__ noisy,
                                float* __restrict__ sigma, int B, int n) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * n) return;
   const int b = (int)(i / n);
@@ -604,6 +826,8 @@ __global__ void diffuse_kernel(const float* __restrict__ clean, const float* __r
 __global__ void __launch_bounds__(256)
 to_uint8_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ std,
                 uint8_t* __restrict__ out, int B, int C, int HW) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * HW) return;
   const int b = (int)(i / HW), p = (int)(i - (long long)b * HW);
@@ -621,7 +845,7 @@ int to_uint8_images(const float* x, const float* mean, const float* std, uint8_t
   const long long n = (long long)B * HW;
   if (n <= 0) return 0;
   TEDM_CHECK(C >= 1 && C <= 16, "to_uint8_images: unsupported channel count %d", C);
-  to_uint8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, mean, std, out, B, C, HW);
+  launch_pdl(to_uint8_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, x, mean, std, out, B, C, HW);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
@@ -647,43 +871,43 @@ int sgemm(const float* A, const float* B, float* C, int M, int N, int K, int lda
     TEDM_CHECK(ldc == N, "sgemm: split-K needs a dense C");
     TEDM_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, stream));
   }
-  sgemm_kernel<<<grid, 256, 0, stream>>>(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, alpha, beta, k_chunk);
+  launch_pdl(sgemm_kernel, grid, 256, 0, stream, A, B, C, M, N, K, lda, ldb, ldc, transA, transB, alpha, beta, k_chunk);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
 
 int embedding_forward(const EmbeddingArgs& a, cudaStream_t stream) {
   TEDM_CHECK(a.B > 0 && a.F > 0 && a.E > 0, "embedding: empty problem");
-  embedding_fwd_kernel<<<a.B, 256, a.F * sizeof(float), stream>>>(a);
+  launch_pdl(embedding_fwd_kernel, a.B, 256, a.F * sizeof(float), stream, a);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
 int embedding_backward(const EmbeddingBwdArgs& a, cudaStream_t stream) {
-  embedding_bwd_kernel<<<a.B, 256, 0, stream>>>(a);
+  launch_pdl(embedding_bwd_kernel, a.B, 256, 0, stream, a);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
 int mod_finish_forward(const float* lin, const float* const* gains, const int* col_block, float* m, int B, int N,
                        cudaStream_t stream) {
   const long long n = (long long)B * N;
-  mod_finish_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(lin, gains, col_block, m, B, N);
+  launch_pdl(mod_finish_fwd_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, lin, gains, col_block, m, B, N);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
 int mod_finish_backward(const float* lin, const float* dm, const float* const* gains, const int* blk_start, float* d_lin,
                         float* d_gain, int B, int N, int n_blocks, cudaStream_t stream) {
   dim3 grid(n_blocks, B < 32 ? (B < 1 ? 1 : B) : 32);
-  mod_finish_bwd_kernel<<<grid, 256, 0, stream>>>(lin, dm, gains, blk_start, d_lin, d_gain, B, N);
+  launch_pdl(mod_finish_bwd_kernel, grid, 256, 0, stream, lin, dm, gains, blk_start, d_lin, d_gain, B, N);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
 int scalelong_forward(const ScaleLongArgs& a, cudaStream_t stream) {
-  scalelong_fwd_kernel<<<a.B, 256, (a.C + 1 + a.R) * sizeof(float), stream>>>(a);
+  launch_pdl(scalelong_fwd_kernel, a.B, 256, (a.C + 1 + a.R) * sizeof(float), stream, a);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
 int scalelong_backward(const ScaleLongBwdArgs& a, cudaStream_t stream) {
-  scalelong_bwd_kernel<<<a.B, 256, (a.C + a.R) * sizeof(float), stream>>>(a);
+  launch_pdl(scalelong_bwd_kernel, a.B, 256, (a.C + a.R) * sizeof(float), stream, a);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
@@ -692,17 +916,17 @@ int scalelong_wgrad(const float* d_pre2, const float* h, const float* d_hpre, co
   if (B <= 0) return 0;
   const int n = C * R + R * (C + 1);
   dim3 grid((n + 255) / 256, B >= 64 ? 8 : 1);
-  scalelong_wgrad_kernel<<<grid, 256, 0, stream>>>(d_pre2, h, d_hpre, aug, dw2, dw1, B, C, R);
+  launch_pdl(scalelong_wgrad_kernel, grid, 256, 0, stream, d_pre2, h, d_hpre, aug, dw2, dw1, B, C, R);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
 int uncertainty_forward(const UncertaintyArgs& a, cudaStream_t stream) {
-  uncertainty_fwd_kernel<<<a.B, 256, (2 * a.F + 1) * sizeof(float), stream>>>(a);
+  launch_pdl(uncertainty_fwd_kernel, a.B, 256, (2 * a.F + 1) * sizeof(float), stream, a);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
 int uncertainty_backward(const UncertaintyBwdArgs& a, cudaStream_t stream) {
-  uncertainty_bwd_kernel<<<a.B, 256, 0, stream>>>(a);
+  launch_pdl(uncertainty_bwd_kernel, a.B, 256, 0, stream, a);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
@@ -710,7 +934,7 @@ int conv_in_im2col(const float* noisy, const float* sigma, int sigma_stride, flo
                    int Ci, int H, int W, cudaStream_t stream) {
   TEDM_CHECK(9 * (Ci + 1) <= 64, "conv_in: at most 6 image channels supported (got %d)", Ci);
   const long long total = (long long)B * H * W * 8;
-  conv_in_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(noisy, sigma, sigma_stride, sigma_data, out, B,
+  launch_pdl(conv_in_im2col_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, noisy, sigma, sigma_stride, sigma_data, out, B,
                                                                             Ci, H, W);
   TEDM_LAUNCH_CHECK();
   return 0;
@@ -718,7 +942,19 @@ int conv_in_im2col(const float* noisy, const float* sigma, int sigma_stride, flo
 int conv_out_forward(const ConvOutArgs& a, cudaStream_t stream) {
   TEDM_CHECK(a.Co >= 1 && a.Co <= kMaxCo && a.C % 64 == 0, "conv_out: unsupported Co=%d C=%d", a.Co, a.C);
   const long long npix = (long long)a.B * a.HW;
-  conv_out_fwd_kernel<<<(unsigned)((npix + 7) / 8), 256, 0, stream>>>(a);
+  if (a.C <= 256) {
+    long long blocks = (npix + 63) / 64;  // 8 pixels per warp and trip
+    if (blocks > 2 * num_sms()) blocks = 2 * num_sms();
+    if (blocks < 1) blocks = 1;
+    switch (a.Co) {
+      case 1: launch_pdl(conv_out_fwd_kernel<1>, (unsigned)blocks, 256, 0, stream, a); break;
+      case 2: launch_pdl(conv_out_fwd_kernel<2>, (unsigned)blocks, 256, 0, stream, a); break;
+      case 3: launch_pdl(conv_out_fwd_kernel<3>, (unsigned)blocks, 256, 0, stream, a); break;
+      default: launch_pdl(conv_out_fwd_kernel<4>, (unsigned)blocks, 256, 0, stream, a); break;
+    }
+  } else {
+    launch_pdl(conv_out_fwd_generic_kernel, (unsigned)((npix + 7) / 8), 256, 0, stream, a);
+  }
   TEDM_LAUNCH_CHECK();
   return 0;
 }
@@ -730,7 +966,19 @@ int conv_out_backward(const ConvOutBwdArgs& a, cudaStream_t stream) {
   if (blocks < 1) blocks = 1;
   const size_t smem = (size_t)8 * a.Co * a.C * sizeof(float);
   TEDM_CHECK(smem <= 48 * 1024, "conv_out_bwd: C too large");
-  conv_out_bwd_kernel<<<(unsigned)blocks, 256, smem, stream>>>(a);
+  if (a.C <= 256) {
+    blocks = (npix + 255) / 256;          // 32 pixels per warp and trip
+    if (blocks > 2 * num_sms()) blocks = 2 * num_sms();
+    if (blocks < 1) blocks = 1;
+    switch (a.Co) {
+      case 1: launch_pdl(conv_out_bwd_kernel<1>, (unsigned)blocks, 256, smem, stream, a); break;
+      case 2: launch_pdl(conv_out_bwd_kernel<2>, (unsigned)blocks, 256, smem, stream, a); break;
+      case 3: launch_pdl(conv_out_bwd_kernel<3>, (unsigned)blocks, 256, smem, stream, a); break;
+      default: launch_pdl(conv_out_bwd_kernel<4>, (unsigned)blocks, 256, smem, stream, a); break;
+    }
+  } else {
+    launch_pdl(conv_out_bwd_generic_kernel, (unsigned)blocks, 256, smem, stream, a);
+  }
   TEDM_LAUNCH_CHECK();
   return 0;
 }
@@ -739,7 +987,7 @@ int wmse_forward(const float* D, const float* y, const float* sigma, const float
   TEDM_CHECK(weight != nullptr || sigma != nullptr, "wmse: need either explicit weights or sigma");
   TEDM_CHECK(B > 0 && n > 0, "wmse: empty batch");
   TEDM_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), stream));
-  wmse_fwd_kernel<<<B, 256, 0, stream>>>(D, y, sigma, u, weight, sigma_data, mse, wsum, loss, B, n);
+  launch_pdl(wmse_fwd_kernel, B, 256, 0, stream, D, y, sigma, u, weight, sigma_data, mse, wsum, loss, B, n);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
@@ -748,20 +996,20 @@ int wmse_backward(const float* D, const float* y, const float* sigma, const floa
                   cudaStream_t stream) {
   TEDM_CHECK(weight != nullptr || sigma != nullptr, "wmse: need either explicit weights or sigma");
   dim3 grid((n + 1023) / 1024 < 1 ? 1 : (n + 1023) / 1024, B);
-  wmse_bwd_kernel<<<grid, 256, 0, stream>>>(D, y, sigma, u, weight, mse, g_loss, sigma_data, g_D, g_u, g_weight, B, n);
+  launch_pdl(wmse_bwd_kernel, grid, 256, 0, stream, D, y, sigma, u, weight, mse, g_loss, sigma_data, g_D, g_u, g_weight, B, n);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
 int heun_step(const float* x0, const float* x1, const float* D, const float* d_prev, float* x_out, float* d_out,
               const float* ts, int step, int mode, long long n, cudaStream_t stream) {
-  heun_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x0, x1, D, d_prev, x_out, d_out, ts, step, mode, n);
+  launch_pdl(heun_step_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, x0, x1, D, d_prev, x_out, d_out, ts, step, mode, n);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
 int diffuse(const float* clean, const float* eps, const float* noise, float P_mean, float P_std, float* noisy,
             float* sigma, int B, int n, cudaStream_t stream) {
   const long long tot = (long long)B * n;
-  diffuse_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(clean, eps, noise, P_mean, P_std, noisy, sigma, B, n);
+  launch_pdl(diffuse_kernel, (unsigned)((tot + 255) / 256), 256, 0, stream, clean, eps, noise, P_mean, P_std, noisy, sigma, B, n);
   TEDM_LAUNCH_CHECK();
   return 0;
 }

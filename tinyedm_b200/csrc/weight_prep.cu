@@ -86,6 +86,8 @@ constexpr int kTileStride = kTileElems + 1;   // odd stride: conflict-free colum
 //           row-per-CTA version wrote 2-byte elements 512 bytes apart and reached 11-16 % of HBM bandwidth.
 __global__ void __launch_bounds__(kFwdThreads)
 weight_prep_fwd_kernel(const WeightDesc* __restrict__ table, int n_tensors, int training) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   __shared__ float tile[kGroupRows * kTileStride];
   __shared__ float s_s1[kGroupRows], s_inv[kGroupRows];
   const int ti = find_group_tensor(table, n_tensors, blockIdx.x);
@@ -217,6 +219,8 @@ weight_prep_fwd_kernel(const WeightDesc* __restrict__ table, int n_tensors, int 
 // global access is coalesced.
 __global__ void __launch_bounds__(kThreads)
 weight_prep_bwd_kernel(const WeightDesc* __restrict__ table, int n_tensors) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   extern __shared__ float grow[];   // [taps][cin + 1]
   __shared__ float red[kThreads / 32];
   const int ti = find_tensor(table, n_tensors, blockIdx.x);
@@ -264,7 +268,7 @@ weight_prep_bwd_kernel(const WeightDesc* __restrict__ table, int n_tensors) {
 
 int weight_prep_forward(const WeightDesc* table_dev, int n_tensors, int total_groups, int training, cudaStream_t stream) {
   if (total_groups <= 0) return 0;
-  weight_prep_fwd_kernel<<<total_groups, kFwdThreads, 0, stream>>>(table_dev, n_tensors, training);
+  launch_pdl(weight_prep_fwd_kernel, total_groups, kFwdThreads, 0, stream, table_dev, n_tensors, training);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
@@ -278,7 +282,7 @@ int weight_prep_backward(const WeightDesc* table_dev, int n_tensors, int total_r
     TEDM_CUDA(cudaFuncSetAttribute(weight_prep_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  weight_prep_bwd_kernel<<<total_rows, kThreads, smem, stream>>>(table_dev, n_tensors);
+  launch_pdl(weight_prep_bwd_kernel, total_rows, kThreads, smem, stream, table_dev, n_tensors);
   TEDM_LAUNCH_CHECK();
   return 0;
 }

@@ -81,3 +81,13 @@ if den is not None:
     report("weight_prep fwd (train: rewrite + 2 bf16 layouts)  r 4P, w 4P+2P+2P", 12 * Pn, lambda: (bank.invalidate(), bank.prepare(True)))
     report("weight_prep fwd (eval)                           r 4P, w 2P+2P", 8 * Pn, lambda: (bank.invalidate(), bank._build_table() if bank._table is None else None, ops.weight_prep_forward(bank._table, len(bank.slots), bank.total_groups, False)))
     report("weight_prep bwd                                  r 4P+4P, w 4P", 12 * Pn, lambda: bank.backward())
+
+# conv_out (+ output preconditioning) and its adjoint at the CIFAR training shape
+Hh = 32; C = 256; Co = 3
+x = rb(B, Hh, Hh, C); w = (torch.randn(Co, C, device=dev) / 16).to(BF); gain_out = torch.tensor(0.8, device=dev)
+noisy = torch.randn(B, Co, Hh, Hh, device=dev); sigma = torch.rand(B, device=dev) + 0.1
+n = B * Hh * Hh * C * 2; ni = B * Co * Hh * Hh * 4
+report("[32x32] conv_out fwd + precond                        r C, r/w image", n + 3 * ni, lambda: ops.conv_out_forward(x, w, gain_out, noisy, sigma, 0.5, True))
+D, f_raw = ops.conv_out_forward(x, w, gain_out, noisy, sigma, 0.5, True)
+g_D = torch.randn_like(D); g_w = torch.zeros(Co, C, device=dev); g_g = torch.zeros((), device=dev)
+report("[32x32] conv_out bwd                                  r C, w C, r image", 2 * n + 2 * ni, lambda: ops.conv_out_backward(g_D, f_raw, x, w, gain_out, sigma, 0.5, g_w, g_g))

@@ -47,17 +47,20 @@ table(prof, "gpurun_out/kernels_train.txt")
 
 # the graph-replayed step: busy time vs span (launch gaps that remain inside the graph)
 def gaps(prof, tag):
-    evs = sorted(((e.time_range.start, e.time_range.end) for e in prof.events() if e.device_time_total > 0 and e.time_range.end > e.time_range.start))
+    evs = sorted(((e.time_range.start, e.time_range.end, e.name) for e in prof.events() if e.device_time_total > 0 and e.time_range.end > e.time_range.start))
     if not evs:
         return
     span = evs[-1][1] - evs[0][0]
-    busy, cur_end, idle_small, idle_big, n_big = 0.0, evs[0][0], 0.0, 0.0, 0
-    for a, b in evs:
+    busy, cur_end, idle_small, idle_big, n_big, prev = 0.0, evs[0][0], 0.0, 0.0, 0, ""
+    for a, b, name in evs:
         if a > cur_end:
             g = a - cur_end
-            if g > 5: idle_big += g; n_big += 1
+            if g > 5:
+                idle_big += g; n_big += 1
+                print(f"   gap {g:8.1f} us at +{(cur_end - evs[0][0])/1e3:7.2f} ms between [{prev[:70]}] and [{name[:70]}]")
             else: idle_small += g
-        busy += max(0.0, b - max(a, cur_end)); cur_end = max(cur_end, b)
+        busy += max(0.0, b - max(a, cur_end))
+        if b > cur_end: cur_end = b; prev = name
     print(f"{tag}: span {span/1e3:.2f} ms, busy {busy/1e3:.2f} ms, idle in gaps<=5us {idle_small/1e3:.2f} ms, idle in {n_big} gaps>5us {idle_big/1e3:.2f} ms, {len(evs)} device activities")
 gaps(prof, "eager step")
 gstep = T.GraphedTrainStep(model, opt, (x, y))
