@@ -55,3 +55,30 @@ def test_attention_forward_backward_vs_torch(dev, B, H, W, heads, hd):
     (g_ref,) = torch.autograd.grad(ref, x, g_y.float().view(B, H * W, C))
     rg = rel(g_qkv.view(B, H * W, 3 * C), g_ref)
     assert rg < 3e-2, rg
+
+
+@pytest.mark.parametrize("B,heads", [(2, 4), (3, 1), (41, 4), (5, 3)])
+def test_attention_backward_s256_each_gradient(dev, B, heads):
+    """S = 256, head_dim 64 (the fused one-CTA-per-head backward): dq, dk and dv separately against fp32 autograd,
+    more (image, head) pairs than SMs in one case so that CTAs are reused."""
+    from tinyedm_b200 import ops
+    ops.ensure_device(dev)
+    torch.manual_seed(7 * B + heads)
+    hd, H, W = 64, 16, 16
+    C = heads * hd
+    qkv = (torch.randn(B, H, W, 3 * C, device=dev) * 1.3).to(torch.bfloat16)
+    y, lse = ops.attention_forward(qkv, heads, need_lse=True)
+    g_y = torch.randn(B, H, W, C, device=dev).to(torch.bfloat16)
+    g_qkv = ops.attention_backward(qkv, y, g_y, lse, heads).view(B, H * W, 3, C).float()
+    x = qkv.float().view(B, H * W, 3 * C).requires_grad_(True)
+    with torch.backends.cuda.sdp_kernel(enable_flash=False, enable_mem_efficient=False, enable_math=True):
+        ref = reference(x, heads)
+    (g_ref,) = torch.autograd.grad(ref, x, g_y.float().view(B, H * W, C))
+    g_ref = g_ref.view(B, H * W, 3, C)
+    assert torch.isfinite(g_qkv).all()
+    for part, name in enumerate("qkv"):
+        r = rel(g_qkv[:, :, part], g_ref[:, :, part])
+        assert r < 1.5e-2, (name, r)
+    # deterministic: no atomics anywhere in the backward
+    again = ops.attention_backward(qkv, y, g_y, lse, heads).view(B, H * W, 3, C).float()
+    assert torch.equal(again, g_qkv)

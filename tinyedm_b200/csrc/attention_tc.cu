@@ -19,6 +19,7 @@
 //                 the softmax has already consumed; commit frees the ring slot                        -> p_free[slot], bar_o
 //     warps 0..3  O / rowsum -> bf16 -> y, log-sum-exp -> lse
 // The S x S score matrix exists only in TMEM and, 64 keys at a time as bf16 P, in shared memory.
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -750,6 +751,274 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmap_t, const __grid_
   }
 }
 
+
+// =====================================================================================================================
+// Fused backward for S = 256: ONE CTA per (image, head) computes dQ, dK and dV. The transposed scores are computed once
+// per (key block, query chunk) and feed all three gradient GEMMs, so q/k/v/dO are loaded and normalised once and every
+// exponential is evaluated once (the two-kernel version above does each of those twice and launches 4x the CTAs).
+//   unit u = (j, i, h): key block j (128 keys = TMEM lanes), query chunk (i, h) = 64 queries 128 i + 64 h ..
+//     MMA      S^T_u = Kn_j Qn_u^T, dP^T_u = Vn_j dO_u^T        (M=128, N=64, K=64) -> 2-slot TMEM rings
+//     threads  P^T = exp2(S^T c - lse_q), dS^T = P^T (dP^T - delta_q)/sqrt(hd) -> bf16, swizzled [128 keys][64 queries]
+//     MMA      dVn_j += P^T_u dO_u,  dKn_j += dS^T_u Qn_u        (M=128 keys, N=64, K=64 queries)
+//              dQn_i += dS_(j,i) Kn_j after both chunks of the block: A = the two dS^T chunks read MN-major
+//                                                                 (M=128 queries, N=64, K=128 keys)
+// TMEM (512 columns): S^T ring 2x64 | dP^T ring 2x64 | dVn_j 64 | dKn_j 64 | dQn_0 64 | dQn_1 64. dVn_0 / dKn_0 are
+// drained (norm adjoint + store) after the 4 units of key block 0, before block 1 reuses their columns.
+// Shared memory: Q, K, V, dO 4 x 32 KB | P^T ring 2 x 16 KB | dS^T ring 4 x 16 KB (a block's two chunks stay until
+// its dQ MMA has read them) | lse, delta vectors.
+// =====================================================================================================================
+constexpr int kFuOffQ = 0, kFuOffK = 32768, kFuOffV = 65536, kFuOffDO = 98304, kFuOffPT = 131072, kFuOffDST = 163840,
+              kFuOffVec = 229376, kFuOffBars = 229376 + 2048;
+constexpr int kFuSmem = kFuOffBars + 128;
+static_assert(kFuSmem <= 232448, "shared memory budget");
+constexpr uint32_t kFuColS = 0, kFuColDP = 128, kFuColDV = 256, kFuColDK = 320, kFuColDQ = 384;
+
+__global__ void __launch_bounds__(kThreadsB, 1)
+attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmap_all, const __grid_constant__ CUtensorMap tmap_do_all,
+                         const __nv_bfloat16* __restrict__ y, const float* __restrict__ lse,
+                         __nv_bfloat16* __restrict__ g_qkv, int heads, float scale) {
+  constexpr int S = 256, NU = 8;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFuOffBars);
+  uint64_t* bar_load = bars;
+  uint64_t* bar_s = bars + 1;        // [2] S^T / dP^T of a unit are in TMEM ring slot u & 1
+  uint64_t* p_ready = bars + 3;      // [2] 256 threads wrote P^T / dS^T of a unit (and are done with its TMEM slot)
+  uint64_t* mma_done = bars + 5;     // [2] every MMA issued up to and including the unit's gradient MMAs completed
+  uint64_t* kv_drained = bars + 7;   // 256 threads read dVn_0 / dKn_0 out of TMEM
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  float* lse_s = reinterpret_cast<float*>(smem + kFuOffVec);
+  float* dl_s = lse_s + 256;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // uniform warp index
+  const int C = heads * kHD;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (threadIdx.x == 0) pdl_trigger();
+  const int pair = blockIdx.x;
+  const int b = pair / heads, head = pair - b * heads;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_all);
+      tma_prefetch_desc(&tmap_do_all);
+      mbar_init(bar_load, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bar_s[i], 1);
+        mbar_init(&p_ready[i], 256);
+        mbar_init(&mma_done[i], 1);
+      }
+      mbar_init(kv_drained, 256);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();   // the prologue above overlapped the previous kernel's tail; its results are needed from here on
+
+  // norms of the rows whose gradients this thread finishes: two rows of K (sub 0) or V (sub 1), one row of Q
+  float n_kv[2] = {1.f, 1.f}, n_q = 1.f;
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_load, 4 * 32768);
+      tma_load_2d(smem + kFuOffQ, &tmap_all, bar_load, head * kHD, b * S);
+      tma_load_2d(smem + kFuOffK, &tmap_all, bar_load, C + head * kHD, b * S);
+      tma_load_2d(smem + kFuOffV, &tmap_all, bar_load, 2 * C + head * kHD, b * S);
+      tma_load_2d(smem + kFuOffDO, &tmap_do_all, bar_load, head * kHD, b * S);
+    }
+  } else {
+    const int r = threadIdx.x;                    // query row 0..255 owned by this thread for lse / delta / Q norm
+    const int sub = threadIdx.x >> 7, m = threadIdx.x & 127;
+    const uint4* orow = reinterpret_cast<const uint4*>(y + ((long long)b * S + r) * C + head * kHD);
+    uint4 ov[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ov[j] = orow[j];
+    lse_s[r] = lse[(long long)pair * S + r] * kLog2eA;
+    mbar_wait_bounded(bar_load, 0);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint4 g = *prow(smem + kFuOffDO, r, j);
+      const float2 g0 = unpack_bf16(g.x), g1 = unpack_bf16(g.y), g2 = unpack_bf16(g.z), g3 = unpack_bf16(g.w);
+      const float2 o0 = unpack_bf16(ov[j].x), o1 = unpack_bf16(ov[j].y), o2 = unpack_bf16(ov[j].z), o3 = unpack_bf16(ov[j].w);
+      acc += g0.x * o0.x + g0.y * o0.y + g1.x * o1.x + g1.y * o1.y + g2.x * o2.x + g2.y * o2.y + g3.x * o3.x + g3.y * o3.y;
+    }
+    dl_s[r] = acc;                                // delta = rowsum(dO o O)
+    n_q = normalize_row_n(smem + kFuOffQ, r);
+    uint8_t* kv = smem + (sub == 0 ? kFuOffK : kFuOffV);
+    n_kv[0] = normalize_row_n(kv, m);
+    n_kv[1] = normalize_row_n(kv, 128 + m);
+    fence_proxy_async_smem();
+  }
+  __syncthreads();
+
+  if (warp == 8) {
+    if (lane == 0) {
+      tc_fence_after();
+      const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);     // K-major A and B
+      const uint32_t idesc_g = make_idesc_bf16(128, kHD, 0, 1);    // K-major A (P^T / dS^T chunk), MN-major B (dO / Q rows)
+      const uint32_t idesc_q = make_idesc_bf16(128, kHD, 1, 1);    // MN-major A (dS^T chunks read as dS), MN-major B (K rows)
+      auto issue_scores = [&](int u) {
+        const int j = u >> 2, qc = u & 3;       // query chunk (i, h) = 64 qc ..
+        const uint32_t slot = (uint32_t)(u & 1) * 64;
+        {
+          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem + kFuOffK + j * 16384), 0, 1024);
+          const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem + kFuOffQ + qc * 8192), 0, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + kFuColS + slot, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc_s, k != 0 ? 1u : 0u);
+        }
+        {
+          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem + kFuOffV + j * 16384), 0, 1024);
+          const uint64_t b_desc = make_smem_desc_sw128(smem_u32(smem + kFuOffDO + qc * 8192), 0, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + kFuColDP + slot, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc_s, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&bar_s[u & 1]);
+      };
+      issue_scores(0);
+      issue_scores(1);
+#pragma unroll 1
+      for (int u = 0; u < NU; ++u) {
+        const int j = u >> 2, qc = u & 3, i = qc >> 1, h = qc & 1;
+        mbar_wait_bounded(&p_ready[u & 1], (u >> 1) & 1);
+        tc_fence_after();
+        if (u + 2 < NU) issue_scores(u + 2);
+        if (u == 4) {                                // dVn_0 / dKn_0 must have left TMEM before block 1 overwrites them
+          mbar_wait_bounded(kv_drained, 0);
+          tc_fence_after();
+        }
+        const uint64_t ap_desc = make_smem_desc_sw128(smem_u32(smem + kFuOffPT + (u & 1) * kPChunkBytes), 0, 1024);
+        const uint64_t as_desc = make_smem_desc_sw128(smem_u32(smem + kFuOffDST + (u & 3) * kPChunkBytes), 0, 1024);
+        const uint64_t bdo_desc = make_smem_desc_sw128(smem_u32(smem + kFuOffDO + qc * 8192), 64 * 128, 1024);
+        const uint64_t bq_desc = make_smem_desc_sw128(smem_u32(smem + kFuOffQ + qc * 8192), 64 * 128, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // dVn_j += P^T_u dO_u
+          umma_bf16(tmem_base + kFuColDV, ap_desc + (uint64_t)(k * 2), bdo_desc + (uint64_t)(k * 128), idesc_g, (qc | k) != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // dKn_j += dS^T_u Qn_u
+          umma_bf16(tmem_base + kFuColDK, as_desc + (uint64_t)(k * 2), bq_desc + (uint64_t)(k * 128), idesc_g, (qc | k) != 0 ? 1u : 0u);
+        if (h == 1) {                 // dQn_i += dS_(j,i) Kn_j : A = chunks (i,0), (i,1) of this block, 16 KB apart
+          const uint64_t a_desc = make_smem_desc_sw128(smem_u32(smem + kFuOffDST + ((u & 3) - 1) * kPChunkBytes), kPChunkBytes, 1024);
+          const uint64_t bk_desc = make_smem_desc_sw128(smem_u32(smem + kFuOffK + j * 16384), 64 * 128, 1024);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tmem_base + kFuColDQ + (uint32_t)i * 64, a_desc + (uint64_t)(k * 128), bk_desc + (uint64_t)(k * 128), idesc_q,
+                      (j | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&mma_done[u & 1]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int sub = warp >> 2;                        // which 32 queries of each 64-query chunk this thread converts
+    const int m = q * 32 + lane;                      // key row within the block = TMEM lane
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float sc = scale * kLog2eA;
+    __nv_bfloat16* gq_base = g_qkv + (long long)b * S * 3 * C + head * kHD;
+    // sub 0 finishes dK rows, sub 1 dV rows (block j: key 128 j + m)
+    auto drain_kv = [&](int j) {
+      uint32_t g0[32], g1[32];
+      const uint32_t col = sub == 0 ? kFuColDK : kFuColDV;
+      tmem_ld32(t_row + col, g0);
+      tmem_ld32(t_row + col + 32, g1);
+      tmem_ld_wait();
+      if (j == 0) {
+        tc_fence_before();
+        mbar_arrive(kv_drained);
+      }
+      const int key = 128 * j + m;
+      norm_adjoint_store(g0, g1, smem + (sub == 0 ? kFuOffK : kFuOffV), key, n_kv[j],
+                         gq_base + (long long)key * 3 * C + (sub == 0 ? C : 2 * C));
+    };
+#pragma unroll 1
+    for (int u = 0; u < NU; ++u) {
+      const int qc = u & 3;
+      uint8_t* pbuf = smem + kFuOffPT + (u & 1) * kPChunkBytes;
+      uint8_t* sbuf = smem + kFuOffDST + (u & 3) * kPChunkBytes;
+      mbar_wait_bounded(&bar_s[u & 1], (u >> 1) & 1);
+      tc_fence_after();
+      uint32_t rs[32], rp[32];
+      tmem_ld32(t_row + kFuColS + (uint32_t)(u & 1) * 64 + sub * 32, rs);
+      tmem_ld32(t_row + kFuColDP + (uint32_t)(u & 1) * 64 + sub * 32, rp);
+      tmem_ld_wait();
+      // the ring slots written below were last read by the MMAs of unit u - 2 (P^T) and of the block two back (dS^T)
+      if (u >= 2) mbar_wait_bounded(&mma_done[u & 1], ((u - 2) >> 1) & 1);
+      const float* lq = lse_s + qc * 64 + sub * 32;
+      const float* dq_ = dl_s + qc * 64 + sub * 32;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float pv[8], dv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = g * 8 + e;
+          pv[e] = exp2f(fmaf(__uint_as_float(rs[c]), sc, -lq[c]));
+          dv[e] = pv[e] * (__uint_as_float(rp[c]) - dq_[c]) * scale;
+        }
+        uint4 o;
+        o.x = pack_bf16(pv[0], pv[1]); o.y = pack_bf16(pv[2], pv[3]); o.z = pack_bf16(pv[4], pv[5]); o.w = pack_bf16(pv[6], pv[7]);
+        *prow(pbuf, m, sub * 4 + g) = o;
+        o.x = pack_bf16(dv[0], dv[1]); o.y = pack_bf16(dv[2], dv[3]); o.z = pack_bf16(dv[4], dv[5]); o.w = pack_bf16(dv[6], dv[7]);
+        *prow(sbuf, m, sub * 4 + g) = o;
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&p_ready[u & 1]);
+      if (u == 3) {                                   // key block 0 is complete once the MMAs of unit 3 are
+        mbar_wait_bounded(&mma_done[1], 1);
+        tc_fence_after();
+        drain_kv(0);
+      }
+    }
+    mbar_wait_bounded(&mma_done[1], 1);               // unit 7: parity (7 >> 1) & 1
+    tc_fence_after();
+    drain_kv(1);
+    {  // dQ: sub 0 finishes queries 0..127 (accumulator 0), sub 1 queries 128..255 (accumulator 1)
+      uint32_t g0[32], g1[32];
+      tmem_ld32(t_row + kFuColDQ + (uint32_t)sub * 64, g0);
+      tmem_ld32(t_row + kFuColDQ + (uint32_t)sub * 64 + 32, g1);
+      tmem_ld_wait();
+      const int qr = 128 * sub + m;
+      norm_adjoint_store(g0, g1, smem + kFuOffQ, qr, n_q, gq_base + (long long)qr * 3 * C);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int launch_bwd_fused(const __nv_bfloat16* qkv, const __nv_bfloat16* y, const __nv_bfloat16* g_y, const float* lse,
+                     __nv_bfloat16* g_qkv, int B, int heads, cudaStream_t stream) {
+  constexpr int S = 256;
+  const int C = heads * kHD;
+  CUtensorMap t_all, t_do_all;
+  {
+    uint64_t dims[2] = {(uint64_t)3 * C, (uint64_t)B * S};
+    uint64_t strides[1] = {(uint64_t)3 * C * 2};
+    uint32_t box[2] = {64, (uint32_t)S};
+    if (encode_tmap(&t_all, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) != 0) return -1;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)C, (uint64_t)B * S};
+    uint64_t strides[1] = {(uint64_t)C * 2};
+    uint32_t box[2] = {64, (uint32_t)S};
+    if (encode_tmap(&t_do_all, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, g_y, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) != 0) return -1;
+  }
+  static unsigned long long configured = 0;
+  if (first_use_on_device(&configured)) {
+    TEDM_CUDA(cudaFuncSetAttribute(attn_bwd_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmem));
+  }
+  TEDM_CUDA(launch_pdl(attn_bwd_fused_tc_kernel, B * heads, kThreadsB, kFuSmem, stream, t_all, t_do_all, y, lse, g_qkv, heads,
+                       1.0f / sqrtf((float)kHD)));
+  return 0;
+}
+
 template <int S>
 int launch_bwd_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* y, const __nv_bfloat16* g_y, const float* lse, float* delta,
                   __nv_bfloat16* g_qkv, int B, int heads, cudaStream_t stream) {
@@ -813,6 +1082,9 @@ bool attention_tc_supported(int S, int hd) { return hd == kHD && (S == 256 || S 
 
 int attention_backward_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* y, const __nv_bfloat16* g_y, const float* lse,
                           float* delta, __nv_bfloat16* g_qkv, int B, int S, int heads, cudaStream_t stream) {
+  // TEDM_ATTN_BWD_FUSED=0 falls back to the two-kernel version (A/B switch)
+  static const bool fused = [] { const char* e = getenv("TEDM_ATTN_BWD_FUSED"); return !(e != nullptr && e[0] == '0'); }();
+  if (S == 256 && fused) return launch_bwd_fused(qkv, y, g_y, lse, g_qkv, B, heads, stream);
   if (S == 256) return launch_bwd_tc<256>(qkv, y, g_y, lse, delta, g_qkv, B, heads, stream);
   return launch_bwd_tc<64>(qkv, y, g_y, lse, delta, g_qkv, B, heads, stream);
 }
