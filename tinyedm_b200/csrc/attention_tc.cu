@@ -807,35 +807,40 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmap_all, const __g
       }
       mbar_init(kv_drained, 256);
       mbar_fence_init();
-    }
-    __syncwarp();
-    tmem_alloc(tmem_ptr, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  pdl_wait();   // the prologue above overlapped the previous kernel's tail; its results are needed from here on
-
-  // norms of the rows whose gradients this thread finishes: two rows of K (sub 0) or V (sub 1), one row of Q
-  float n_kv[2] = {1.f, 1.f}, n_q = 1.f;
-  if (warp == 8) {
-    if (lane == 0) {
+      // the 128 KB of operands are requested before anything else (the issuing thread initialised the barrier itself)
+      pdl_wait();
       mbar_expect_tx(bar_load, 4 * 32768);
       tma_load_2d(smem + kFuOffQ, &tmap_all, bar_load, head * kHD, b * S);
       tma_load_2d(smem + kFuOffK, &tmap_all, bar_load, C + head * kHD, b * S);
       tma_load_2d(smem + kFuOffV, &tmap_all, bar_load, 2 * C + head * kHD, b * S);
       tma_load_2d(smem + kFuOffDO, &tmap_do_all, bar_load, head * kHD, b * S);
     }
-  } else {
-    const int r = threadIdx.x;                    // query row 0..255 owned by this thread for lse / delta / Q norm
-    const int sub = threadIdx.x >> 7, m = threadIdx.x & 127;
+    __syncwarp();
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  // O row and log-sum-exp of this thread's query: in flight across the TMEM allocation / CTA barrier
+  uint4 ov[8];
+  float lse_r = 0.f;
+  if (warp != 8) {
+    pdl_wait();
+    const int r = threadIdx.x;
     const uint4* orow = reinterpret_cast<const uint4*>(y + ((long long)b * S + r) * C + head * kHD);
-    uint4 ov[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) ov[j] = orow[j];
-    lse_s[r] = lse[(long long)pair * S + r] * kLog2eA;
+    lse_r = lse[(long long)pair * S + r];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // norms of the rows whose gradients this thread finishes: two rows of K (sub 0) or V (sub 1), one row of Q
+  float n_kv[2] = {1.f, 1.f}, n_q = 1.f;
+  if (warp != 8) {
+    const int r = threadIdx.x;                    // query row 0..255 owned by this thread for lse / delta / Q norm
+    const int sub = threadIdx.x >> 7, m = threadIdx.x & 127;
+    lse_s[r] = lse_r * kLog2eA;
     mbar_wait_bounded(bar_load, 0);
     float acc = 0.f;
 #pragma unroll
@@ -967,7 +972,7 @@ attn_bwd_fused_tc_kernel(const __grid_constant__ CUtensorMap tmap_all, const __g
       tc_fence_before();
       fence_proxy_async_smem();
       mbar_arrive(&p_ready[u & 1]);
-      if (u == 3) {                                   // key block 0 is complete once the MMAs of unit 3 are
+      if (u == 4) {   // key block 0 is complete once the MMAs of unit 3 are; by now (one unit later) they have retired
         mbar_wait_bounded(&mma_done[1], 1);
         tc_fence_after();
         drain_kv(0);

@@ -409,14 +409,20 @@ class DenoiserEngine:
         if save:
             ctx = dict(B=B, H=H, W=W, noisy=noisy, sigma=sigma, emb=emb, lin=lin, mod=mod, xcol=xcol, blocks=[],
                        drop_p=drop_p, Be=Be)
+        # ScaleLong's per-(image, channel) mean of a skip tensor (networks.py:112) is taken as soon as the tensor exists,
+        # while the producing kernel's output is still (partly) in L2, not when the decoder pops it much later
+        used = self._skips_consumed()
         skips = [x]
+        means = [self._skip_mean(x) if used[0] else None]
         for bp in self.blocks:
-            skip = None
+            skip = mean = None
             if bp.kind == "dec" and bp.cskip > 0:
                 skip = skips.pop()
-            x, saved = self._block_forward(bp, x, skip, mod, mod_stride, drop_p, save)
+                mean = means.pop()
+            x, saved = self._block_forward(bp, x, skip, mod, mod_stride, drop_p, save, mean)
             if bp.kind == "enc":
                 skips.append(x)
+                means.append(self._skip_mean(x) if used[len(skips) - 1] else None)
             if save:
                 ctx["blocks"].append(saved)
             if taps is not None:
@@ -427,8 +433,29 @@ class DenoiserEngine:
             ctx["f_raw"] = f_raw
         return D, ctx
 
+    def _skips_consumed(self) -> list[bool]:
+        """used[i]: the i-th tensor pushed on the skip stack (conv_in output, then every encoder block's) is popped by a
+        decoder block with a skip connection."""
+        if getattr(self, "_skip_used", None) is None:
+            stack, used, n = [0], {}, 1
+            for bp in self.blocks:
+                if bp.kind == "dec" and bp.cskip > 0:
+                    used[stack.pop()] = True
+                if bp.kind == "enc":
+                    stack.append(n)
+                    n += 1
+            self._skip_used = [used.get(i, False) for i in range(n)]
+        return self._skip_used
+
+    @staticmethod
+    def _skip_mean(x: Tensor) -> Tensor:
+        B, H, W, C = x.shape
+        mean = torch.zeros((B, C), device=x.device, dtype=F32)
+        ops.channel_dot(x, None, mean, C, 0, 1.0 / (H * W))
+        return mean
+
     def _block_forward(self, bp: BlockPlan, xin: Tensor, skip: Tensor | None, mod: Tensor, mod_stride: int,
-                       drop_p: float, save: bool):
+                       drop_p: float, save: bool, skip_mean: Tensor | None = None):
         S: dict = {}
         B, Hin, Win, _ = xin.shape
         S["in_shape"] = (B, Hin, Win)
@@ -447,8 +474,7 @@ class DenoiserEngine:
         else:
             if skip is not None:
                 Cs = bp.cskip
-                mean = torch.zeros((B, Cs), device=xin.device, dtype=F32)
-                ops.channel_dot(skip, None, mean, Cs, 0, 1.0 / (Hin * Win))
+                mean = skip_mean if skip_mean is not None else self._skip_mean(skip)
                 aug, h_pre, hh, gain = ops.scalelong_forward(mean, bp.w["sl1"].f32, bp.w["sl2"].f32, bp.w["sl1"].rows)
                 x, a, _ = ops.block_prep(xin, skip=skip, gain=gain, resample=bp.resample)
                 S.update(skip=skip, aug=aug, h_pre=h_pre, hh=hh, gain=gain)
