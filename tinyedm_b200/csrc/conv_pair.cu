@@ -309,7 +309,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const bool use_old = (EPI == EPI_SILU_BWD) && p.accumulate_out;
     const bool two_sweep = (EPI == EPI_SILU_BWD) && p.nrm != nullptr;
     // a single output buffer that is not refilled by TMA needs an explicit "previous store has been read" hand-shake
-    const bool top_barrier = (EPI == EPI_MODSILU) || (EPI == EPI_SILU_BWD && !use_old);
+    const bool top_barrier = (EPI == EPI_SILU_BWD && !use_old);
+    // MODSILU: h ping-pongs between buf1 and buf2 like the outputs of the kPingPong epilogues; the raw copy (training only)
+    // goes through buf0 and is written after h, behind a mid-chunk "previous stores have been read" hand-shake that has
+    // had a whole chunk of work to complete
+    const bool modsilu_raw = (EPI == EPI_MODSILU) && p.out2 != nullptr;
 
     auto tile_range = [&](int ptile, int& cb, int& ce) {
       const int n0 = (ptile % p.n_tiles) * kBN;
@@ -408,7 +412,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           in_phase ^= 1;
         }
         uint8_t* obuf = (EPI == EPI_PLAIN) ? ((qi & 1) ? buf1 : buf0)
-                        : (kPingPong ? ((qi & 1) ? buf2 : buf1) : (EPI == EPI_MODSILU ? buf1 : buf2));
+                        : ((kPingPong || EPI == EPI_MODSILU) ? ((qi & 1) ? buf2 : buf1) : buf2);
 #pragma unroll 1
         for (int s = 0; s < kStepsPerWarp; ++s) {
           const int col_in_chunk = sub * (64 / kSub) + s * CW;
@@ -427,7 +431,6 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
             for (int i = 0; i < CW; ++i) v[i] = bf16_round(v[i]);
             if (row_ok) {
-              if (p.out2 != nullptr) srow_store<CW>(buf0, m, j0, v);
               const float* mrow = p.mod + (long long)b * p.mod_stride + n0 + cc;
 #pragma unroll
               for (int g = 0; g < CW / 4; ++g) {
@@ -438,7 +441,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 v[g * 4 + 3] = mp_silu_f(v[g * 4 + 3] * mm.w);
               }
               if (p.drop_p > 0.f) dropout_apply<CW>(v, (unsigned long long)pix * p.Cout + n0 + cc, p.drop_p, dseed);
-              srow_store<CW>(buf1, m, j0, v);
+              srow_store<CW>(obuf, m, j0, v);
             }
           } else if constexpr (EPI == EPI_AXPBY) {
             if (row_ok) {
@@ -525,8 +528,25 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
         if (sweep1) tmem_st_wait();
+        if (modsilu_raw) {
+          // un-modulated conv output (bf16) for the backward pass: second, cheap read of the accumulator columns
+          if (elected) bulk_wait_read0();
+          named_bar_sync(bar_half, kHalfThreads);
+#pragma unroll 1
+          for (int s = 0; s < kStepsPerWarp; ++s) {
+            const int col_in_chunk = sub * (64 / kSub) + s * CW;
+            uint32_t r[CW];
+            tmem_ld_cw(t_row + pos.c * 64 + col_in_chunk, r);
+            tmem_ld_wait();
+            float v[CW];
+#pragma unroll
+            for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+            if (row_ok) srow_store<CW>(buf0, m, col_in_chunk / 8, v);
+          }
+        }
         if (writes_out) fence_proxy_async_smem();
-        if (kPingPong && elected) bulk_wait_read0();   // the store issued one chunk ago has released the other buffer
+        // the store issued one chunk ago has released the other buffer
+        if ((kPingPong || (EPI == EPI_MODSILU && !modsilu_raw)) && elected) bulk_wait_read0();
         named_bar_sync(bar_half, kHalfThreads);
         ChunkPos nx = pos;
         advance(nx);
