@@ -37,24 +37,41 @@ sgemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* _
   const int k_end = min(K, k_begin + k_chunk);
   const bool split = gridDim.z > 1;
   float acc[4][4] = {};
-  for (int k0 = k_begin; k0 < k_end; k0 += TK) {
-    for (int i = threadIdx.x; i < TS * TK; i += 256) {
+  // register-staged global loads: the tile of step k+1 is in flight while step k is multiplied out of shared memory
+  float ra[4], rb[4];
+  auto load_tile = [&](int k0) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int i = threadIdx.x + t * 256;
       int mm, kk;
       if (transA) { mm = i % TS; kk = i / TS; } else { kk = i % TK; mm = i / TK; }
       const int gm = m0 + mm, gk = k0 + kk;
-      float v = 0.f;
-      if (gm < M && gk < k_end) v = transA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
-      As[kk][mm] = v;
+      ra[t] = 0.f;
+      if (gm < M && gk < k_end) ra[t] = transA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+      int nn, kb;
+      if (transB) { kb = i % TK; nn = i / TK; } else { nn = i % TS; kb = i / TS; }
+      const int gn = n0 + nn, gkb = k0 + kb;
+      rb[t] = 0.f;
+      if (gn < N && gkb < k_end) rb[t] = transB ? Bm[(size_t)gn * ldb + gkb] : Bm[(size_t)gkb * ldb + gn];
     }
-    for (int i = threadIdx.x; i < TS * TK; i += 256) {
-      int nn, kk;
-      if (transB) { kk = i % TK; nn = i / TK; } else { nn = i % TS; kk = i / TS; }
-      const int gn = n0 + nn, gk = k0 + kk;
-      float v = 0.f;
-      if (gn < N && gk < k_end) v = transB ? Bm[(size_t)gn * ldb + gk] : Bm[(size_t)gk * ldb + gn];
-      Bs[kk][nn] = v;
+  };
+  auto store_tile = [&]() {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int i = threadIdx.x + t * 256;
+      int mm, kk;
+      if (transA) { mm = i % TS; kk = i / TS; } else { kk = i % TK; mm = i / TK; }
+      As[kk][mm] = ra[t];
+      int nn, kb;
+      if (transB) { kb = i % TK; nn = i / TK; } else { nn = i % TS; kb = i / TS; }
+      Bs[kb][nn] = rb[t];
     }
+  };
+  if (k_begin < k_end) load_tile(k_begin);
+  for (int k0 = k_begin; k0 < k_end; k0 += TK) {
+    store_tile();
     __syncthreads();
+    if (k0 + TK < k_end) load_tile(k0 + TK);
 #pragma unroll
     for (int kk = 0; kk < TK; ++kk) {
       const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
