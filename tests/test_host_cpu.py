@@ -133,6 +133,12 @@ def test_engine_plan_matches_the_reference_skip_pairing():
     for bp, ref in zip(eng.blocks, enc_o + dec_o):
         assert (bp.cin, bp.cout) == (ref["cin"], ref["cout"]) and bp.attn == ref["attn"]
         assert bp.cskip == ref.get("cskip", 0)
+    # the skip tensors whose ScaleLong mean is taken at production time are exactly the ones a decoder block pops
+    assert eng._skips_consumed() == [True] * 9
+    for cfg in (O.MNIST, O.IMAGENET):
+        e2 = T.Denoiser(**spec_kwargs(cfg["denoiser"])).engine
+        popped = {bp.skip_src for bp in e2.blocks if bp.cskip > 0}
+        assert [i for i, u in enumerate(e2._skips_consumed()) if u] == sorted(popped)
 
 
 def test_lr_schedule_and_ema_exponent():
