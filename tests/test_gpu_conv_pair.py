@@ -40,7 +40,9 @@ def _silu_grad(x):
 
 # B, H, W, Cin, Cout, ks — pair tiles: (B*H*W/256) * ceil(Cout/256) > 37
 CASES = [(40, 32, 32, 256, 256, 3), (41, 16, 16, 256, 256, 3), (150, 8, 8, 256, 256, 3), (40, 16, 16, 256, 768, 1),
-         (24, 28, 28, 128, 128, 3), (90, 14, 14, 256, 256, 1), (12, 64, 64, 192, 192, 3), (161, 7, 7, 512, 512, 1)]
+         (24, 28, 28, 128, 128, 3), (90, 14, 14, 256, 256, 1), (12, 64, 64, 192, 192, 3), (161, 7, 7, 512, 512, 1),
+         # tail split: 100 resp. 150 pair tiles on 74 CTA pairs leave 26 resp. 2 tiles, cut into half-N work items
+         (100, 16, 16, 256, 256, 3), (50, 16, 16, 256, 768, 1)]
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,ks", CASES)

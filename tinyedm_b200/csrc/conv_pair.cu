@@ -17,6 +17,7 @@
 // TMEM (2 x 256 columns in each CTA).
 #include <mutex>
 
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -133,6 +134,29 @@ __device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t (&r)[32]) { 
 __device__ __forceinline__ void tmem_st_cw(uint32_t taddr, const uint32_t (&r)[16]) { tmem_st16(taddr, r); }
 __device__ __forceinline__ void tmem_st_cw(uint32_t taddr, const uint32_t (&r)[32]) { tmem_st32(taddr, r); }
 
+// Work item -> (pair M-tile, first output channel, channels). The tail of a launch whose whole tiles do not fill the
+// last wave of CTA pairs is cut into half-N items so that the remainder occupies (almost) every pair for half a tile
+// time instead of fewer than half of the pairs for a whole one (16x16 maps at B = 256: 3.5 tile times instead of 4).
+struct NTile { int pmt, n0, n_this; };
+__device__ __forceinline__ NTile decode_item(const ConvGemmParams& p, int item) {
+  int tile = item, half = -1;
+  if (item >= p.split_from) {
+    const int h = item - p.split_from;
+    tile = p.split_from + (h >> 1);
+    half = h & 1;
+  }
+  NTile t;
+  t.pmt = tile / p.n_tiles;
+  t.n0 = (tile - t.pmt * p.n_tiles) * kBN;
+  t.n_this = p.Cout - t.n0;
+  if (t.n_this > kBN) t.n_this = kBN;
+  if (half >= 0) {           // only whole 256-channel tiles are split (host side guarantees Cout % 256 == 0)
+    t.n_this >>= 1;
+    t.n0 += half * t.n_this;
+  }
+  return t;
+}
+
 // Position of one epilogue half (4 warps) in its stream of 64-channel chunks.
 struct ChunkPos {
   int ptile;   // pair tile
@@ -167,7 +191,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t rank = cluster_ctarank();
   const int cid = (int)cluster_id_x();
   const int ncl = (int)num_clusters_x();
-  const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  const int pair_tiles = p.work_items;   // whole pair tiles, then (optionally) half-N items: see decode_item
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -214,12 +238,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t tx_pair = 2 * (a_bytes + kBHalfBytes);
       const int kc_per_tap = p.Cin / kBK;
       for (int ptile = cid; ptile < pair_tiles; ptile += ncl) {
-        const int pmt = ptile / p.n_tiles;
-        const int n0 = (ptile - pmt * p.n_tiles) * kBN;
-        int n_this = p.Cout - n0;
-        if (n_this > kBN) n_this = kBN;
-        const MTile t = decode_m(p, 2 * pmt + (int)rank);
-        const int b_row = n0 + (int)rank * (n_this >> 1);
+        const NTile nt = decode_item(p, ptile);
+        const MTile t = decode_m(p, 2 * nt.pmt + (int)rank);
+        const int b_row = nt.n0 + (int)rank * (nt.n_this >> 1);
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dr = (p.taps == 9) ? tap / 3 - 1 : 0;
           const int ds = (p.taps == 9) ? tap % 3 - 1 : 0;
@@ -252,10 +273,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t acc_phase = 0;
       const uint32_t smem_base = smem_u32(smem);
       for (int ptile = cid; ptile < pair_tiles; ptile += ncl) {
-        const int n0 = (ptile % p.n_tiles) * kBN;
-        int n_this = p.Cout - n0;
-        if (n_this > kBN) n_this = kBN;
-        const uint32_t idesc = make_idesc_bf16(2 * kBM, n_this, 0, 0);
+        const uint32_t idesc = make_idesc_bf16(2 * kBM, decode_item(p, ptile).n_this, 0, 0);
         mbar_wait_bounded(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kBN;
@@ -316,10 +334,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const bool modsilu_raw = (EPI == EPI_MODSILU) && p.out2 != nullptr;
 
     auto tile_range = [&](int ptile, int& cb, int& ce) {
-      const int n0 = (ptile % p.n_tiles) * kBN;
-      int n_this = p.Cout - n0;
-      if (n_this > kBN) n_this = kBN;
-      const int nch = n_this >> 6;
+      const int nch = decode_item(p, ptile).n_this >> 6;
       const int h0n = (nch + 1) >> 1;
       cb = half == 0 ? 0 : h0n;
       ce = half == 0 ? h0n : nch;
@@ -337,10 +352,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     };
     // operands of chunk `s` -> shared memory (issued by the elected thread of the half)
     auto issue_loads = [&](const ChunkPos& s) {
-      const int pmt = s.ptile / p.n_tiles;
-      const int n0 = (s.ptile - pmt * p.n_tiles) * kBN;
-      const MTile t = decode_m(p, 2 * pmt + (int)rank);
-      const int c0 = n0 + s.c * 64;
+      const NTile nt = decode_item(p, s.ptile);
+      const MTile t = decode_m(p, 2 * nt.pmt + (int)rank);
+      const int c0 = nt.n0 + s.c * 64;
       if constexpr (EPI == EPI_AXPBY || EPI == EPI_MODSILU_BWD) {
         mbar_expect_tx(my_in_full, box_bytes);
         tma_load_4d(buf0, &tmap_i0, my_in_full, c0, 0, t.h0, t.b0);
@@ -387,11 +401,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     while (pos.valid) {
       if (pos.ptile != cur_tile) {
         cur_tile = pos.ptile;
-        const int pmt = pos.ptile / p.n_tiles;
-        n0 = (pos.ptile - pmt * p.n_tiles) * kBN;
-        n_this = p.Cout - n0;
-        if (n_this > kBN) n_this = kBN;
-        t = decode_m(p, 2 * pmt + (int)rank);
+        const NTile nt = decode_item(p, pos.ptile);
+        n0 = nt.n0;
+        n_this = nt.n_this;
+        t = decode_m(p, 2 * nt.pmt + (int)rank);
         pix = t.p_base + m;
         valid = row_ok && pix < t.p_limit;
         b = valid ? (int)(pix / HW) : 0;
@@ -764,6 +777,15 @@ int conv_pair_launch(const ConvGemmArgs& a, cudaStream_t stream) {
   const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
   int clusters = num_sms() / 2;
   if (clusters > pair_tiles) clusters = pair_tiles;
+  // tail split (see decode_item): the remainder tiles of the last wave become half-N items when that fills the wave
+  // better. Not with the fused pixel-norm adjoint, whose row dot needs all channels of a pixel in one CTA.
+  p.split_from = p.work_items = pair_tiles;
+  const int rem = pair_tiles % clusters;
+  static const bool tail_split = [] { const char* e = getenv("TEDM_CONV_TAIL_SPLIT"); return !(e != nullptr && e[0] == '0'); }();
+  if (tail_split && rem > 0 && 2 * rem <= clusters && pair_tiles > clusters && a.Cout % kBN == 0 && a.nrm == nullptr) {
+    p.split_from = pair_tiles - rem;
+    p.work_items = pair_tiles + rem;
+  }
   switch (a.epi) {
     case EPI_PLAIN: return launch_pair<EPI_PLAIN>(maps, p, clusters, stream);
     case EPI_MODSILU: return launch_pair<EPI_MODSILU>(maps, p, clusters, stream);

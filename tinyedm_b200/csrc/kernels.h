@@ -64,6 +64,9 @@ struct ConvGemmParams {
   float* d_mod;
   const float* nrm;
   int accumulate_out;
+  // conv_pair.cu only: work items [0, split_from) are whole pair tiles, items [split_from, work_items) are HALF-N
+  // tiles (two consecutive items = the two 128-channel halves of one pair tile); split_from == work_items: no split
+  int split_from, work_items;
 };
 
 int conv_tile_geometry(int H, int W, int* RH, int* NB);
