@@ -96,7 +96,9 @@ int tedm_channel_dot(const void* A, const void* Bm, float* out, int B, int HW, i
  * qkv: (B,S,3C) bf16 with channel = {q,k,v}*C + head*hd + d (the layout the qkv conv emits when its weight rows are
  * permuted by the weight bank, see tedm_weight_desc.qkv_head_dim); y: (B,S,C), channel = head*hd + d (networks.py:202);
  * lse: (B*heads*S) fp32 log-sum-exp kept for backward (may be NULL in inference). The normalisation and its
- * backward are fused into the kernels: no normalised copy of q,k,v exists in HBM. delta_ws: (B*heads*S) fp32. */
+ * backward are fused into the kernels: no normalised copy of q,k,v exists in HBM. delta_ws: (B*heads*S) fp32 scratch
+ * (rowsum(dO o O); the fused S = 256, head_dim 64 backward keeps it in shared memory and leaves the buffer untouched).
+ * The backward uses no atomics: results are bit-reproducible. */
 int tedm_attention_forward(const void* qkv, void* y, float* lse, int B, int S, int heads, int head_dim,
                            tedm_stream_t stream);
 int tedm_attention_backward(const void* qkv, const void* y, const void* g_y, const float* lse, float* delta_ws,

@@ -1,4 +1,5 @@
-// Cosine-normalised self-attention forward on tcgen05/TMEM (sm_100a), head_dim 64, S = 256 or 64 keys per head.
+// Cosine-normalised self-attention on tcgen05/TMEM (sm_100a), head_dim 64: forward for S = 256 or 64 keys per head,
+// backward for S = 256 (fused one-CTA-per-head kernel; the older two-kernel version behind TEDM_ATTN_BWD_FUSED=0).
 //
 // Reference: CosineAttention.forward, src/tinyedm/networks.py:191-207 — pixel_norm over hd of q, k and v (:195), then
 // F.scaled_dot_product_attention(q, k, v) with scale 1/sqrt(hd) (:201), output channel = head*hd + d (:202).

@@ -129,9 +129,10 @@ __device__ __forceinline__ void dropout_apply(float (&v)[N], unsigned long long 
   }
 }
 
-__device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
+// the 16-column overloads serve kSub = 2 (16 epilogue warps per CTA), kept selectable at compile time
+[[maybe_unused]] __device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
 __device__ __forceinline__ void tmem_ld_cw(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
-__device__ __forceinline__ void tmem_st_cw(uint32_t taddr, const uint32_t (&r)[16]) { tmem_st16(taddr, r); }
+[[maybe_unused]] __device__ __forceinline__ void tmem_st_cw(uint32_t taddr, const uint32_t (&r)[16]) { tmem_st16(taddr, r); }
 __device__ __forceinline__ void tmem_st_cw(uint32_t taddr, const uint32_t (&r)[32]) { tmem_st32(taddr, r); }
 
 // Work item -> (pair M-tile, first output channel, channels). The tail of a launch whose whole tiles do not fill the
