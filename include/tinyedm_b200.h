@@ -69,6 +69,22 @@ int tedm_conv2d_forward(const void* x, const void* w, void* out, int B, int H, i
                         int epilogue, float alpha, void* raw, const void* res, float beta, const float* mod,
                         int mod_stride, float drop_p, uint64_t seed, const uint64_t* seed_ptr, int block_n,
                         const void* aux, float* d_mod, const float* nrm, int accumulate_out, tedm_stream_t stream);
+/* Data gradient of conv_3x3_1 of a decoder block WITH a skip connection, whose input is cat(in, skip*gain)
+ * (networks.py:309-316 and autograd): epilogue 4 over the C1+C2 concatenated channels, g_cat = alpha*dgrad *
+ * mp_silu'(x) + beta*res, split in the epilogue instead of materialising g_cat:
+ *   g_in  (B,H,W,C1)  (= | += when accumulate_in)  g_cat[..., :C1]
+ *   g_skip(B,H,W,C2)   =  g_cat[..., C1:] * gain[b,:]          (the ScaleLong mean-gradient share is added later with
+ *                                                                tedm_bias_add_bc once d gain is known)
+ *   d_gx  (B,C2)      +=  sum_pixels g_cat[..., C1:] * x[..., C1:]   = d gain * gain (x holds skip*gain); zero it first
+ * g: gradient w.r.t. the conv output (B,H,W,Cin); w: the out_dgrad weight layout [C1+C2][k*k][Cin]; x, res: (B,H,W,C1+C2).
+ * Only the CTA-pair kernel implements it: ask tedm_conv2d_dgrad_split_supported (returns 1 / 0) first. */
+int tedm_conv2d_dgrad_split_supported(int B, int H, int W, int Cin, int C1, int C2, int ksize);
+int tedm_conv2d_dgrad_split(const void* g, const void* w, void* g_in, void* g_skip, int B, int H, int W, int Cin, int C1,
+                            int C2, int ksize, float alpha, const void* x, const void* res, float beta, const float* gain,
+                            float* d_gx, int accumulate_in, tedm_stream_t stream);
+/* g[b,p,c] += scale * bias[b,c]  (bf16 NHWC tensor, fp32 per-(image, channel) bias): the gradient of ScaleLong's
+ * spatial mean (networks.py:112) with scale = 1/HW */
+int tedm_bias_add_bc(void* g, const float* bias, float scale, int B, int HW, int C, tedm_stream_t stream);
 /* dL/dw_hat of the convolution above: dw[co][tap][ci] (=|+=) alpha * sum_p g[p,co] * x[p+tap,ci]  (autograd of :37) */
 int tedm_conv2d_wgrad(const void* g, const void* x, float* dw, int B, int H, int W, int Cin, int Cout, int ksize,
                       float alpha, int accumulate, int splits, tedm_stream_t stream);
@@ -124,7 +140,8 @@ int tedm_mod_finish_backward(const float* lin, const float* dm, const void* gain
 int tedm_scalelong_forward(const float* mean, const float* w1, const float* w2, float* aug, float* h_pre, float* h,
                            float* gain, int B, int C, int R, tedm_stream_t stream);
 int tedm_scalelong_backward(const float* d_gain, const float* gain, const float* h_pre, const float* w1, const float* w2,
-                            float* d_pre2, float* d_hpre, float* d_mean, int B, int C, int R, tedm_stream_t stream);
+                            float* d_pre2, float* d_hpre, float* d_mean, int B, int C, int R, int d_gain_times_gain,
+                            tedm_stream_t stream);
 /* sample post-processing (callbacks.py:152-154, datamodule.denormalize): out[b,h,w,c] = uint8(clamp(x[b,c,h,w] * std[c] * 2
  * + mean[c], 0, 1) * 255), x fp32 NCHW (the sampler's output), out uint8 NHWC (what PIL / the PNG writer consumes) */
 int tedm_to_uint8_images(const float* x, const float* mean, const float* std, void* out, int B, int C, int HW,

@@ -42,6 +42,37 @@ int tedm_conv2d_forward(const void* x, const void* w, void* out, int B, int H, i
   return conv_gemm_launch(a, static_cast<cudaStream_t>(stream));
 }
 
+static ConvGemmArgs dgrad_split_args(int B, int H, int W, int Cin, int C1, int C2, int ksize) {
+  ConvGemmArgs a{};
+  a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = C1 + C2; a.ksize = ksize;
+  a.epi = EPI_SILU_BWD;
+  a.split_c = C1;
+  return a;
+}
+int tedm_conv2d_dgrad_split_supported(int B, int H, int W, int Cin, int C1, int C2, int ksize) {
+  if (C1 <= 0 || C2 <= 0) return 0;
+  return conv_split_supported(dgrad_split_args(B, H, W, Cin, C1, C2, ksize)) ? 1 : 0;
+}
+int tedm_conv2d_dgrad_split(const void* g, const void* w, void* g_in, void* g_skip, int B, int H, int W, int Cin, int C1,
+                            int C2, int ksize, float alpha, const void* x, const void* res, float beta, const float* gain,
+                            float* d_gx, int accumulate_in, tedm_stream_t stream) {
+  ConvGemmArgs a = dgrad_split_args(B, H, W, Cin, C1, C2, ksize);
+  a.x = static_cast<const __nv_bfloat16*>(g);
+  a.w = static_cast<const __nv_bfloat16*>(w);
+  a.out = static_cast<__nv_bfloat16*>(g_in);
+  a.out2 = static_cast<__nv_bfloat16*>(g_skip);
+  a.alpha = alpha;
+  a.aux = static_cast<const __nv_bfloat16*>(x);
+  a.res = static_cast<const __nv_bfloat16*>(res);
+  a.beta = beta;
+  a.mod = gain; a.mod_stride = C2; a.d_mod = d_gx;
+  a.accumulate_out = accumulate_in;
+  return conv_gemm_launch(a, static_cast<cudaStream_t>(stream));
+}
+int tedm_bias_add_bc(void* g, const float* bias, float scale, int B, int HW, int C, tedm_stream_t stream) {
+  return bias_add_bc(static_cast<__nv_bfloat16*>(g), bias, scale, B, HW, C, static_cast<cudaStream_t>(stream));
+}
+
 int tedm_conv2d_wgrad(const void* g, const void* x, float* dw, int B, int H, int W, int Cin, int Cout, int ksize,
                       float alpha, int accumulate, int splits, tedm_stream_t stream) {
   ConvWgradArgs a{};
@@ -129,8 +160,9 @@ int tedm_scalelong_forward(const float* mean, const float* w1, const float* w2, 
   return scalelong_forward(a, ST(stream));
 }
 int tedm_scalelong_backward(const float* d_gain, const float* gain, const float* h_pre, const float* w1, const float* w2,
-                            float* d_pre2, float* d_hpre, float* d_mean, int B, int C, int R, tedm_stream_t stream) {
-  ScaleLongBwdArgs a{d_gain, gain, h_pre, w1, w2, d_pre2, d_hpre, d_mean, B, C, R};
+                            float* d_pre2, float* d_hpre, float* d_mean, int B, int C, int R, int d_gain_times_gain,
+                            tedm_stream_t stream) {
+  ScaleLongBwdArgs a{d_gain, gain, h_pre, w1, w2, d_pre2, d_hpre, d_mean, B, C, R, d_gain_times_gain};
   return scalelong_backward(a, ST(stream));
 }
 int tedm_to_uint8_images(const float* x, const float* mean, const float* std, void* out, int B, int C, int HW,

@@ -492,8 +492,17 @@ static int conv_pair_mode() {
   return mode;
 }
 
+bool conv_split_supported(const ConvGemmArgs& a) {
+  return conv_pair_mode() == 1 && a.B > 0 && a.nrm == nullptr && a.split_c > 0 && a.split_c % 64 == 0 && a.split_c < a.Cout &&
+         conv_pair_supported(a);
+}
+
 int conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t stream) {
   TEDM_CHECK(a.ksize == 1 || a.ksize == 3, "conv_gemm: kernel size must be 1 or 3 (got %d)", a.ksize);
+  if (a.split_c > 0) {   // the split epilogue exists in the CTA-pair kernel only (callers ask conv_split_supported first)
+    TEDM_CHECK(conv_split_supported(a), "conv_gemm: split epilogue not available for this problem");
+    return conv_pair_launch(a, stream);
+  }
   if (a.block_n_override == 0 && conv_pair_mode() == 1 && a.B > 0 && conv_pair_supported(a) &&
       (a.nrm != nullptr || 4 * conv_pair_tiles(a) > num_sms()))   // at least half of the CTA pairs get a tile
     return conv_pair_launch(a, stream);

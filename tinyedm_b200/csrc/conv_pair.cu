@@ -198,7 +198,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_o);
-    if (EPI == EPI_MODSILU && p.out2 != nullptr) tma_prefetch_desc(&tmap_o2);
+    if ((EPI == EPI_MODSILU || EPI == EPI_SILU_BWD) && p.out2 != nullptr) tma_prefetch_desc(&tmap_o2);
     if (EPI == EPI_AXPBY || EPI == EPI_MODSILU_BWD || EPI == EPI_SILU_BWD) tma_prefetch_desc(&tmap_i0);
     if (EPI == EPI_SILU_BWD && p.res != nullptr) tma_prefetch_desc(&tmap_i1);
   }
@@ -327,8 +327,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const bool use_res = (EPI == EPI_SILU_BWD) && p.res != nullptr;
     const bool use_old = (EPI == EPI_SILU_BWD) && p.accumulate_out;
     const bool two_sweep = (EPI == EPI_SILU_BWD) && p.nrm != nullptr;
-    // a single output buffer that is not refilled by TMA needs an explicit "previous store has been read" hand-shake
-    const bool top_barrier = (EPI == EPI_SILU_BWD && !use_old);
+    // split epilogue (ConvGemmArgs::split_c): chunks of the skip half never load an old value
+    const int split_c = (EPI == EPI_SILU_BWD && p.split_c > 0) ? p.split_c : (1 << 30);
+    auto chunk_old = [&](int c0) { return use_old && c0 < split_c; };
     // MODSILU: h ping-pongs between buf1 and buf2 like the outputs of the kPingPong epilogues; the raw copy (training only)
     // goes through buf0 and is written after h, behind a mid-chunk "previous stores have been read" hand-shake that has
     // had a whole chunk of work to complete
@@ -361,7 +362,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tma_load_4d(buf0, &tmap_i0, my_in_full, c0, 0, t.h0, t.b0);
       } else if constexpr (EPI == EPI_SILU_BWD) {
         const bool ld_res = use_res && !(two_sweep && s.pass == 1);
-        const bool ld_old = use_old && !(two_sweep && s.pass == 0);
+        const bool ld_old = chunk_old(c0) && !(two_sweep && s.pass == 0);
         if (ld_old) bulk_wait_read0();   // the store that last read buf2 must be done before TMA overwrites it
         mbar_expect_tx(my_in_full, box_bytes * (1u + (ld_res ? 1u : 0u) + (ld_old ? 1u : 0u)));
         tma_load_4d(buf0, &tmap_i0, my_in_full, c0, 0, t.h0, t.b0);
@@ -417,7 +418,9 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (pos.cb < pos.ce) {
         const bool sweep1 = two_sweep && pos.pass == 0;   // accumulates the row dot, parks v in TMEM, writes nothing
         const bool writes_out = !sweep1;
-        if (top_barrier && writes_out) {
+        // a single output buffer that is not refilled by TMA needs an explicit "previous store has been read" hand-shake
+        const bool cur_old = chunk_old(n0 + pos.c * 64);
+        if (EPI == EPI_SILU_BWD && !cur_old && writes_out) {
           if (elected) bulk_wait_read0();
           named_bar_sync(bar_half, kHalfThreads);
         }
@@ -530,8 +533,33 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 r[i] = __float_as_uint(v[i]);
               }
               tmem_st_cw(t_row + cc, r);
+            } else if (n0 + cc >= split_c) {
+              // skip half of a decoder block's concatenated gradient: d(gain)*gain reduction over pixels, then * gain
+              float dg[CW];
+#pragma unroll
+              for (int i = 0; i < CW; ++i) dg[i] = valid ? v[i] * xv[i] : 0.f;
+              const int cs = n0 + cc - split_c;                // first channel within the skip tensor
+              if (valid) {
+                const float* grow_ = p.mod + (long long)b * p.mod_stride + cs;
+#pragma unroll
+                for (int g = 0; g < CW / 4; ++g) {
+                  const float4 gg = *reinterpret_cast<const float4*>(grow_ + g * 4);
+                  v[g * 4 + 0] *= gg.x; v[g * 4 + 1] *= gg.y; v[g * 4 + 2] *= gg.z; v[g * 4 + 3] *= gg.w;
+                }
+              }
+              if (row_ok) srow_store<CW>(buf2, m, j0, v);
+              if (warp_one_image) {
+                const long long pw = t.p_base + q * 32;   // first pixel of this warp's rows
+                const float tot = warp_transpose_reduce<CW>(dg, lane);
+                if (q * 32 < rows_in_tile && pw < t.p_limit && lane < CW && cc + lane < n_this)
+                  atomicAdd(p.d_mod + (long long)(pw / HW) * p.mod_stride + cs + lane, tot);
+              } else if (valid) {
+#pragma unroll
+                for (int i = 0; i < CW; ++i)
+                  if (cc + i < n_this) atomicAdd(p.d_mod + (long long)b * p.mod_stride + cs + i, dg[i]);
+              }
             } else if (row_ok) {
-              if (use_old) {
+              if (cur_old) {
                 float ov[CW];
                 srow_load<CW>(buf2, m, j0, ov);
 #pragma unroll
@@ -567,7 +595,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (elected) {
           if (writes_out) {
             const int c0 = n0 + pos.c * 64;
-            tma_store_4d(&tmap_o, obuf, c0, 0, t.h0, t.b0);
+            if (c0 >= split_c) tma_store_4d(&tmap_o2, obuf, c0 - split_c, 0, t.h0, t.b0);
+            else tma_store_4d(&tmap_o, obuf, c0, 0, t.h0, t.b0);
             if (EPI == EPI_MODSILU && p.out2 != nullptr) tma_store_4d(&tmap_o2, buf0, c0, 0, t.h0, t.b0);
             bulk_commit();
           }
@@ -758,6 +787,11 @@ int conv_pair_launch(const ConvGemmArgs& a, cudaStream_t stream) {
   p.beta = a.beta; p.mod = a.mod; p.mod_stride = a.mod_stride;
   p.drop_p = a.drop_p; p.seed_lo = (uint32_t)a.seed; p.seed_hi = (uint32_t)(a.seed >> 32); p.seed_ptr = a.seed_ptr;
   p.aux = a.aux; p.d_mod = a.d_mod; p.nrm = a.nrm; p.accumulate_out = a.accumulate_out;
+  p.split_c = a.epi == EPI_SILU_BWD ? a.split_c : 0;
+  if (p.split_c > 0)
+    TEDM_CHECK(p.split_c % 64 == 0 && p.split_c < a.Cout && a.out2 != nullptr && a.mod != nullptr && a.d_mod != nullptr &&
+                   a.nrm == nullptr && a.mod_stride >= a.Cout - p.split_c,
+               "conv_pair: split epilogue needs split_c %% 64 == 0, out2, gain, d_gx and no fused pixel norm");
   if (a.epi == EPI_MODSILU) TEDM_CHECK(a.mod != nullptr, "conv_pair: MODSILU epilogue needs mod");
   if (a.epi == EPI_AXPBY) TEDM_CHECK(a.res != nullptr, "conv_pair: AXPBY epilogue needs res");
   if (a.epi == EPI_MODSILU_BWD)
@@ -767,9 +801,10 @@ int conv_pair_launch(const ConvGemmArgs& a, cudaStream_t stream) {
   CUtensorMap maps[6];
   if (nhwc_tmap(&maps[0], a.x, a.Cin, a.W, a.H, a.B, p.RH, p.NB) != 0) return -1;
   if (weight_tmap(&maps[1], a.w, p.taps * a.Cin, a.Cout, kBN / 2) != 0) return -1;
-  if (nhwc_tmap(&maps[2], a.out, a.Cout, a.W, a.H, a.B, p.RH, p.NB) != 0) return -1;
+  if (nhwc_tmap(&maps[2], a.out, p.split_c > 0 ? p.split_c : a.Cout, a.W, a.H, a.B, p.RH, p.NB) != 0) return -1;
   maps[3] = maps[2]; maps[4] = maps[2]; maps[5] = maps[2];
   if (a.epi == EPI_MODSILU && a.out2 != nullptr && nhwc_tmap(&maps[3], a.out2, a.Cout, a.W, a.H, a.B, p.RH, p.NB) != 0) return -1;
+  if (p.split_c > 0 && nhwc_tmap(&maps[3], a.out2, a.Cout - p.split_c, a.W, a.H, a.B, p.RH, p.NB) != 0) return -1;
   const void* in0 = a.epi == EPI_AXPBY ? (const void*)a.res : (const void*)a.aux;
   if ((a.epi == EPI_AXPBY || a.epi == EPI_MODSILU_BWD || a.epi == EPI_SILU_BWD) &&
       nhwc_tmap(&maps[4], in0, a.Cout, a.W, a.H, a.B, p.RH, p.NB) != 0) return -1;

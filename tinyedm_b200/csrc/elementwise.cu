@@ -713,6 +713,41 @@ int modsilu_backward(const ModSiluBwdArgs& a, cudaStream_t stream) {
   return 0;
 }
 
+namespace {
+// g[b,p,c] += scale * bias[b,c]: one thread per 8 channels of a pixel (16-byte accesses)
+__global__ void __launch_bounds__(256)
+bias_add_bc_kernel(__nv_bfloat16* __restrict__ g, const float* __restrict__ bias, float scale, long long nvec, int HW, int C) {
+  pdl_trigger();
+  pdl_wait();
+  const int vpp = C / 8;   // vectors per pixel
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / vpp;
+    const int cv = (int)(i - pix * vpp);
+    const int b = (int)(pix / HW);
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + (size_t)b * C + cv * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias + (size_t)b * C + cv * 8 + 4);
+    uint4 u = *reinterpret_cast<const uint4*>(g + i * 8);
+    const float2 p0 = unpack_bf16(u.x), p1 = unpack_bf16(u.y), p2 = unpack_bf16(u.z), p3 = unpack_bf16(u.w);
+    u.x = pack_bf16(fmaf(scale, b0.x, p0.x), fmaf(scale, b0.y, p0.y));
+    u.y = pack_bf16(fmaf(scale, b0.z, p1.x), fmaf(scale, b0.w, p1.y));
+    u.z = pack_bf16(fmaf(scale, b1.x, p2.x), fmaf(scale, b1.y, p2.y));
+    u.w = pack_bf16(fmaf(scale, b1.z, p3.x), fmaf(scale, b1.w, p3.y));
+    *reinterpret_cast<uint4*>(g + i * 8) = u;
+  }
+}
+}  // namespace
+
+int bias_add_bc(__nv_bfloat16* g, const float* bias, float scale, int B, int HW, int C, cudaStream_t stream) {
+  TEDM_CHECK(C % 8 == 0 && C > 0, "bias_add_bc: C must be a multiple of 8 (got %d)", C);
+  const long long nvec = (long long)B * HW * (C / 8);
+  if (nvec <= 0) return 0;
+  long long blocks = (nvec + 255) / 256;
+  if (blocks > 16LL * num_sms()) blocks = 16LL * num_sms();
+  launch_pdl(bias_add_bc_kernel, (unsigned)blocks, 256, 0, stream, g, bias, scale, nvec, HW, C);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+
 int channel_dot(const ChannelDotArgs& a, cudaStream_t stream) {
   TEDM_CHECK(a.C % 8 == 0 && a.C / 8 <= 256 && a.C > 0 && a.CA % 8 == 0 && a.a_off % 8 == 0, "channel_dot: unsupported C=%d", a.C);
   const int nvec = a.C / 8;

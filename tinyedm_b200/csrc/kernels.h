@@ -43,6 +43,11 @@ struct ConvGemmArgs {
   float* d_mod;              // MODSILU_BWD: (B, mod_stride) fp32, column offset applied, accumulated atomically
   const float* nrm;          // SILU_BWD: (B*H*W) eps + rms of the pixel norm whose adjoint is fused, or null
   int accumulate_out;        // SILU_BWD: out += result
+  // SILU_BWD, CTA-pair kernel only: split the Cout = split_c + C2 output channels of a decoder block's concatenated
+  // input gradient in the epilogue. Channels < split_c go to `out` ((B,H,W,split_c), accumulate_out applies to it);
+  // channels >= split_c are multiplied by gain = mod[b, c - split_c] and go to `out2` ((B,H,W,C2)), and
+  // d_mod[b, c - split_c] += sum_pixels g * x (= d gain * gain, because x holds skip * gain). 0 = off.
+  int split_c;
 };
 
 // Device-side parameter block of the implicit-GEMM kernel.
@@ -67,10 +72,12 @@ struct ConvGemmParams {
   // conv_pair.cu only: work items [0, split_from) are whole pair tiles, items [split_from, work_items) are HALF-N
   // tiles (two consecutive items = the two 128-channel halves of one pair tile); split_from == work_items: no split
   int split_from, work_items;
+  int split_c;   // see ConvGemmArgs::split_c
 };
 
 int conv_tile_geometry(int H, int W, int* RH, int* NB);
 int conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t stream);
+bool conv_split_supported(const ConvGemmArgs& a);   // ConvGemmArgs::split_c > 0 can be honoured (CTA-pair kernel)
 // conv_pair.cu: the CTA-pair (tcgen05 cta_group::2) version with the TMA-staged epilogue
 bool conv_pair_supported(const ConvGemmArgs& a);
 int conv_pair_tiles(const ConvGemmArgs& a);
@@ -196,6 +203,7 @@ struct ScaleLongBwdArgs {
   float* d_hpre;   // (B,R)
   float* d_mean;   // (B,C)
   int B, C, R;
+  int d_gain_times_gain;   // d_gain holds (d gain) * gain (the split conv epilogue's reduction over skip * gain)
 };
 int scalelong_backward(const ScaleLongBwdArgs& a, cudaStream_t stream);
 int scalelong_wgrad(const float* d_pre2, const float* h, const float* d_hpre, const float* aug, float* dw2, float* dw1, int B,
@@ -237,6 +245,7 @@ struct ConvOutBwdArgs {
   int B, HW, C, Co;
 };
 int conv_out_backward(const ConvOutBwdArgs& a, cudaStream_t stream);
+int bias_add_bc(__nv_bfloat16* g, const float* bias, float scale, int B, int HW, int C, cudaStream_t stream);
 int to_uint8_images(const float* x, const float* mean, const float* std, uint8_t* out, int B, int C, int HW, cudaStream_t stream);
 int wmse_forward(const float* D, const float* y, const float* sigma, const float* u, const float* weight, float sigma_data,
                  float* mse, float* wsum, float* loss, int B, int n, cudaStream_t stream);

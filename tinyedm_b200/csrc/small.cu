@@ -249,7 +249,8 @@ scalelong_bwd_kernel(const ScaleLongBwdArgs a) {
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
     const float g = a.gain[(size_t)b * a.C + c];
-    const float v = a.d_gain[(size_t)b * a.C + c] * g * (1.0f - g);
+    // gain = sigmoid(pre2): d pre2 = d gain * g (1 - g); the split conv epilogue already delivers (d gain) * g
+    const float v = a.d_gain[(size_t)b * a.C + c] * (a.d_gain_times_gain ? 1.0f : g) * (1.0f - g);
     dp2[c] = v;
     a.d_pre2[(size_t)b * a.C + c] = v;
   }

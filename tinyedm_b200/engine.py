@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -249,6 +250,11 @@ class BlockPlan:
     in_src: int = -1      # index into the skip list that is this block's input (if its input is a skip source)
     w: dict = field(default_factory=dict)  # name -> WeightSlot
     gain: torch.nn.Parameter | None = None
+
+
+def split_epilogue_enabled() -> bool:
+    """TEDM_SPLIT_EPILOGUE=0 keeps the separate concat-split / gain-gradient kernels in the backward (A/B switch)."""
+    return os.environ.get("TEDM_SPLIT_EPILOGUE", "1") != "0"
 
 
 class DenoiserEngine:
@@ -645,6 +651,22 @@ class DenoiserEngine:
         if bp.cskip == 0 and bp.resample == RESAMPLE_NONE:
             g_in, acc = self._take_g_in(bp, pending, (B, Hin, Win, bp.cin), dev)
             ops.conv2d(g_raw, w1.dgrad, 3, ctot, epi=EPI_SILU_BWD, aux=x, res=g_res, beta=beta, out=g_in, accumulate_out=acc)
+            return g_in
+        if (bp.cskip > 0 and bp.resample == RESAMPLE_NONE and split_epilogue_enabled()
+                and ops.conv2d_dgrad_split_supported(B, Hin, Win, bp.cout, bp.cin, bp.cskip, 3)):
+            # conv1's data gradient, mp_silu', the residual share, the concat split, the ScaleLong gain and the reduction
+            # for d(gain) in ONE kernel: g_cat is never materialised (it used to be written once and read twice)
+            Cs = bp.cskip
+            g_in, acc = self._take_g_in(bp, pending, (B, Hin, Win, bp.cin), dev)
+            g_skip = torch.empty((B, Hin, Win, Cs), device=dev, dtype=BF16)
+            d_gx = torch.zeros((B, Cs), device=dev, dtype=F32)
+            ops.conv2d_dgrad_split(g_raw, w1.dgrad, 3, x=x, res=g_res, beta=beta, gain=S["gain"], g_in=g_in, g_skip=g_skip,
+                                   d_gx=d_gx, accumulate_in=acc)
+            s1, s2 = bp.w["sl1"], bp.w["sl2"]
+            d_pre2, d_hpre, d_mean = ops.scalelong_backward(d_gx, S["gain"], S["h_pre"], s1.f32, s2.f32, d_gain_times_gain=True)
+            ops.scalelong_wgrad(d_pre2, S["hh"], d_hpre, S["aug"], s2.ghat, s1.ghat)   # into the zeroed g_hat buffer
+            ops.bias_add_bc(g_skip, d_mean, 1.0 / (Hin * Win))    # gradient through the spatial mean of [skip, 1]
+            pending[bp.skip_src] = g_skip
             return g_in
         # gradient w.r.t. x on the post-resample grid: conv1's data gradient * mp_silu'(x) + the residual share
         g_x = ops.conv2d(g_raw, w1.dgrad, 3, ctot, epi=EPI_SILU_BWD, aux=x, res=g_res, beta=beta)

@@ -85,6 +85,27 @@ def conv2d(x: Tensor, w: Tensor, ksize: int, cout: int, *, epi: int = EPI_PLAIN,
     return out
 
 
+def conv2d_dgrad_split_supported(B: int, H: int, W: int, cin: int, c1: int, c2: int, ksize: int) -> bool:
+    return _lib.call_int("tedm_conv2d_dgrad_split_supported", B, H, W, cin, c1, c2, ksize) == 1
+
+
+def conv2d_dgrad_split(g: Tensor, w: Tensor, ksize: int, *, x: Tensor, res: Tensor, beta: float, gain: Tensor, g_in: Tensor,
+                       g_skip: Tensor, d_gx: Tensor, accumulate_in: bool, alpha: float = 1.0) -> None:
+    """Data gradient of a skip-decoder block's first conv with the concat split, the ScaleLong gain and the reduction for
+    d(gain) fused into the epilogue (see tedm_conv2d_dgrad_split). d_gx (B,C2) fp32 must be zeroed by the caller."""
+    B, H, W, cin = g.shape
+    c1, c2 = g_in.shape[3], g_skip.shape[3]
+    _lib.call("tedm_conv2d_dgrad_split", g.data_ptr(), w.data_ptr(), g_in.data_ptr(), g_skip.data_ptr(), B, H, W, cin, c1, c2,
+              ksize, alpha, x.data_ptr(), res.data_ptr(), beta, gain.data_ptr(), d_gx.data_ptr(), 1 if accumulate_in else 0,
+              _stream())
+
+
+def bias_add_bc(g: Tensor, bias: Tensor, scale: float) -> None:
+    """g[b,h,w,c] += scale * bias[b,c] in place (bf16 NHWC, fp32 bias)."""
+    B, H, W, C = g.shape
+    _lib.call("tedm_bias_add_bc", g.data_ptr(), bias.data_ptr(), scale, B, H * W, C, _stream())
+
+
 def conv2d_wgrad(g: Tensor, x: Tensor, dw: Tensor, ksize: int, *, alpha: float = 1.0, accumulate: bool = False,
                  splits: int = 0) -> None:
     """dw[cout][k*k][cin] (fp32) (+)= alpha * sum_pixels g x."""
@@ -230,14 +251,15 @@ def scalelong_forward(mean: Tensor, w1: Tensor, w2: Tensor, R: int):
     return aug, h_pre, h, gain
 
 
-def scalelong_backward(d_gain: Tensor, gain: Tensor, h_pre: Tensor, w1: Tensor, w2: Tensor):
+def scalelong_backward(d_gain: Tensor, gain: Tensor, h_pre: Tensor, w1: Tensor, w2: Tensor, d_gain_times_gain: bool = False):
     B, C = gain.shape
     R = h_pre.shape[1]
     d_pre2 = torch.empty_like(gain)
     d_hpre = torch.empty_like(h_pre)
     d_mean = torch.empty_like(gain)
     _lib.call("tedm_scalelong_backward", d_gain.data_ptr(), gain.data_ptr(), h_pre.data_ptr(), w1.data_ptr(),
-              w2.data_ptr(), d_pre2.data_ptr(), d_hpre.data_ptr(), d_mean.data_ptr(), B, C, R, _stream())
+              w2.data_ptr(), d_pre2.data_ptr(), d_hpre.data_ptr(), d_mean.data_ptr(), B, C, R,
+              1 if d_gain_times_gain else 0, _stream())
     return d_pre2, d_hpre, d_mean
 
 
