@@ -68,7 +68,15 @@ int tedm_weight_prep_backward(const tedm_weight_desc* table, int n, int total_ro
 int tedm_conv2d_forward(const void* x, const void* w, void* out, int B, int H, int W, int Cin, int Cout, int ksize,
                         int epilogue, float alpha, void* raw, const void* res, float beta, const float* mod,
                         int mod_stride, float drop_p, uint64_t seed, const uint64_t* seed_ptr, int block_n,
-                        const void* aux, float* d_mod, const float* nrm, int accumulate_out, tedm_stream_t stream);
+                        const void* aux, float* d_mod, const float* nrm, int accumulate_out, float* col_partial,
+                        tedm_stream_t stream);
+/* Epilogues 0 and 2 can also emit per-(image, channel) partial sums of the stored output, so that ScaleLong's spatial
+ * mean of a skip tensor (networks.py:112) needs no pass over the tensor: col_partial is fp32 [B * slots][Cout] with
+ * slots = tedm_conv2d_colsum_slots(...) rows per image (0: not available for this launch - pass NULL and reduce the tensor
+ * with tedm_channel_dot instead). Every entry is written exactly once, without atomics (bit-reproducible).
+ * tedm_colsum_mean: mean[b,c] = scale * sum_s col_partial[b*slots + s, c]. */
+int tedm_conv2d_colsum_slots(int B, int H, int W, int Cin, int Cout, int ksize, int epilogue);
+int tedm_colsum_mean(const float* col_partial, float* mean, int B, int slots, int C, float scale, tedm_stream_t stream);
 /* Data gradient of conv_3x3_1 of a decoder block WITH a skip connection, whose input is cat(in, skip*gain)
  * (networks.py:309-316 and autograd): epilogue 4 over the C1+C2 concatenated channels, g_cat = alpha*dgrad *
  * mp_silu'(x) + beta*res, split in the epilogue instead of materialising g_cat:

@@ -257,7 +257,7 @@ def test_small_denoiser_teacher_forced_blocks(dev, golden):
         for j, bp in enumerate(eng.blocks):
             xin = to_dev(taps[names[j]])
             skip = to_dev(skips[bp.skip_src]) if bp.cskip > 0 else None
-            out, _ = eng._block_forward(bp, xin, skip, mod, eng.n_mod, 0.0, False)
+            out, _, _ = eng._block_forward(bp, xin, skip, mod, eng.n_mod, 0.0, False)
             r = rel(nhwc_to_nchw(out), taps[bp.name])
             worst = max(worst, r)
             assert r < BF16_TOL, (bp.name, r)

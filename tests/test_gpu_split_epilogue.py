@@ -72,3 +72,48 @@ def test_bias_add_bc_matches_torch(dev):
         ref = (g.float() + 0.125 * bias[:, None, None, :]).to(BF)
         ops.bias_add_bc(g, bias, 0.125)
         assert torch.equal(g, ref)
+
+
+@pytest.mark.parametrize("B", [3, 48])
+def test_skip_mean_from_conv_epilogue_matches_channel_dot(dev, B, monkeypatch):
+    """ScaleLong's spatial mean taken from the producing conv's epilogue (fixed-order partial sums) against the separate
+    reduction (TEDM_FUSED_SKIP_MEAN=0); B = 48 is large enough for the CTA-pair kernel at every level of the CIFAR net.
+    Also: the fused path is bit-reproducible (no atomics)."""
+    from tinyedm_b200.configs import CIFAR10, build_edm
+    torch.manual_seed(5)
+    model = build_edm(CIFAR10, num_classes=10, dropout_rate=0.0).to(dev).eval()
+    with torch.no_grad():
+        model.denoiser.gain_out.fill_(1.0)
+    x = torch.randn(B, 3, 32, 32, device=dev)
+    sigma = torch.full((B,), 1.3, device=dev)
+    y = torch.randint(0, 10, (B,), device=dev)
+    with torch.no_grad():
+        monkeypatch.setenv("TEDM_FUSED_SKIP_MEAN", "1")
+        d1 = model(x, sigma, y).clone()
+        d1b = model(x, sigma, y).clone()
+        monkeypatch.setenv("TEDM_FUSED_SKIP_MEAN", "0")
+        d0 = model(x, sigma, y).clone()
+    assert torch.equal(d1, d1b)
+    assert rel(d1, d0) < 2e-3, rel(d1, d0)
+
+
+def test_colsum_partials_equal_the_column_sums(dev):
+    """col_partial of a PLAIN and an AXPBY conv: summed per image it equals the spatial sum of the stored bf16 output."""
+    from tinyedm_b200 import ops
+    from tinyedm_b200.ops import EPI_AXPBY, EPI_PLAIN
+    ops.ensure_device(dev)
+    torch.manual_seed(1)
+    for (B, H, W, Cin, Cout, ks) in [(40, 32, 32, 64, 256, 1), (150, 16, 16, 128, 256, 3), (300, 8, 8, 64, 128, 3)]:
+        x = torch.randn(B, H, W, Cin, device=dev).to(BF)
+        w = (torch.randn(Cout, ks * ks * Cin, device=dev) / (ks * ks * Cin) ** 0.5).to(BF)
+        res = torch.randn(B, H, W, Cout, device=dev).to(BF)
+        for epi, kw in ((EPI_PLAIN, {}), (EPI_AXPBY, dict(alpha=0.6, beta=0.8, res=res))):
+            slots = ops.conv2d_colsum_slots(B, H, W, Cin, Cout, ks, epi)
+            assert slots > 0, (B, H, W, Cin, Cout, ks)
+            part = torch.full((B * slots, Cout), float("nan"), device=dev)
+            out = ops.conv2d(x, w, ks, Cout, epi=epi, col_partial=part, **kw)
+            assert torch.isfinite(part).all()                      # every entry written
+            mean = ops.colsum_mean(part, B, slots, Cout, 1.0 / (H * W))
+            ref = out.float().mean(dim=(1, 2))
+            assert rel(mean, ref) < 1e-5
+            assert torch.equal(out, ops.conv2d(x, w, ks, Cout, epi=epi, **kw))   # the conv result itself is unchanged

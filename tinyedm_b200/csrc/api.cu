@@ -24,7 +24,8 @@ int tedm_init(int device) {
 int tedm_conv2d_forward(const void* x, const void* w, void* out, int B, int H, int W, int Cin, int Cout, int ksize,
                         int epilogue, float alpha, void* raw, const void* res, float beta, const float* mod,
                         int mod_stride, float drop_p, uint64_t seed, const uint64_t* seed_ptr, int block_n,
-                        const void* aux, float* d_mod, const float* nrm, int accumulate_out, tedm_stream_t stream) {
+                        const void* aux, float* d_mod, const float* nrm, int accumulate_out, float* col_partial,
+                        tedm_stream_t stream) {
   ConvGemmArgs a{};
   a.x = static_cast<const __nv_bfloat16*>(x);
   a.w = static_cast<const __nv_bfloat16*>(w);
@@ -39,7 +40,16 @@ int tedm_conv2d_forward(const void* x, const void* w, void* out, int B, int H, i
   a.block_n_override = block_n;
   a.aux = static_cast<const __nv_bfloat16*>(aux);
   a.d_mod = d_mod; a.nrm = nrm; a.accumulate_out = accumulate_out;
+  a.col_partial = col_partial;
   return conv_gemm_launch(a, static_cast<cudaStream_t>(stream));
+}
+int tedm_conv2d_colsum_slots(int B, int H, int W, int Cin, int Cout, int ksize, int epilogue) {
+  ConvGemmArgs a{};
+  a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize; a.epi = epilogue;
+  return conv_colsum_slots(a);
+}
+int tedm_colsum_mean(const float* col_partial, float* mean, int B, int slots, int C, float scale, tedm_stream_t stream) {
+  return colsum_mean(col_partial, mean, B, slots, C, scale, static_cast<cudaStream_t>(stream));
 }
 
 static ConvGemmArgs dgrad_split_args(int B, int H, int W, int Cin, int C1, int C2, int ksize) {

@@ -497,15 +497,25 @@ bool conv_split_supported(const ConvGemmArgs& a) {
          conv_pair_supported(a);
 }
 
+static bool conv_takes_pair(const ConvGemmArgs& a) {
+  return a.block_n_override == 0 && conv_pair_mode() == 1 && a.B > 0 && conv_pair_supported(a) &&
+         (a.nrm != nullptr || 4 * conv_pair_tiles(a) > num_sms());   // at least half of the CTA pairs get a tile
+}
+
+int conv_colsum_slots(const ConvGemmArgs& a) {
+  if ((a.epi != EPI_PLAIN && a.epi != EPI_AXPBY) || !conv_takes_pair(a)) return 0;
+  return conv_pair_colsum_slots(a);
+}
+
 int conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t stream) {
   TEDM_CHECK(a.ksize == 1 || a.ksize == 3, "conv_gemm: kernel size must be 1 or 3 (got %d)", a.ksize);
   if (a.split_c > 0) {   // the split epilogue exists in the CTA-pair kernel only (callers ask conv_split_supported first)
     TEDM_CHECK(conv_split_supported(a), "conv_gemm: split epilogue not available for this problem");
     return conv_pair_launch(a, stream);
   }
-  if (a.block_n_override == 0 && conv_pair_mode() == 1 && a.B > 0 && conv_pair_supported(a) &&
-      (a.nrm != nullptr || 4 * conv_pair_tiles(a) > num_sms()))   // at least half of the CTA pairs get a tile
-    return conv_pair_launch(a, stream);
+  if (a.col_partial != nullptr)
+    TEDM_CHECK(conv_colsum_slots(a) > 0, "conv_gemm: column sums not available for this problem (ask conv_colsum_slots first)");
+  if (conv_takes_pair(a)) return conv_pair_launch(a, stream);
   TEDM_CHECK(a.Cin % 64 == 0, "conv_gemm: Cin must be a multiple of 64 (got %d)", a.Cin);
   TEDM_CHECK(a.Cout % 16 == 0 && a.Cout >= 16, "conv_gemm: Cout must be a multiple of 16 (got %d)", a.Cout);
   TEDM_CHECK(a.B > 0 && a.H > 0 && a.W > 0, "conv_gemm: empty input");

@@ -400,13 +400,25 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t t_row = 0;
     float dot = 0.f, inv_n = 1.f, kk = 0.f;
 
+    int cur_mt = 0;         // M tile of this CTA within the current pair tile
+    // column sums over this warp's 32 rows of the values as stored (bf16), fixed order: see ConvGemmArgs::col_partial
+    auto col_sums = [&](const float (&v)[CW], int cc) {
+      float cs[CW];
+#pragma unroll
+      for (int i = 0; i < CW; ++i) cs[i] = (row_ok && valid) ? bf16_round(v[i]) : 0.f;
+      const float tot = warp_transpose_reduce<CW>(cs, lane);
+      if (cur_mt < p.m_tiles && lane < CW && cc + lane < n_this)
+        p.col_partial[((long long)cur_mt * 4 + q) * p.Cout + n0 + cc + lane] = tot;
+    };
+
     while (pos.valid) {
       if (pos.ptile != cur_tile) {
         cur_tile = pos.ptile;
         const NTile nt = decode_item(p, pos.ptile);
         n0 = nt.n0;
         n_this = nt.n_this;
-        t = decode_m(p, 2 * nt.pmt + (int)rank);
+        cur_mt = 2 * nt.pmt + (int)rank;
+        t = decode_m(p, cur_mt);
         pix = t.p_base + m;
         valid = row_ok && pix < t.p_limit;
         b = valid ? (int)(pix / HW) : 0;
@@ -443,6 +455,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
           if constexpr (EPI == EPI_PLAIN) {
             if (row_ok) srow_store<CW>(obuf, m, j0, v);
+            if (p.col_partial != nullptr) col_sums(v, cc);
           } else if constexpr (EPI == EPI_MODSILU) {
             // the reference's conv output is bf16 before the fp32 modulation island (networks.py:253-258)
 #pragma unroll
@@ -468,6 +481,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               for (int i = 0; i < CW; ++i) v[i] += p.beta * rv[i];
               srow_store<CW>(obuf, m, j0, v);
             }
+            if (p.col_partial != nullptr) col_sums(v, cc);
           } else if constexpr (EPI == EPI_MODSILU_BWD) {
             // backward of h = drop(mp_silu(raw * m)):  gz = g_h * keep/(1-p) * mp_silu'(raw*m);  g_raw = gz * m;
             // d_mod[b,c] += sum_pixels gz * raw
@@ -760,6 +774,16 @@ bool conv_pair_supported(const ConvGemmArgs& a) {
   return true;
 }
 
+// Rows of ConvGemmArgs::col_partial per image (0: the tile geometry does not keep a warp's 32 rows inside one image)
+int conv_pair_colsum_slots(const ConvGemmArgs& a) {
+  int RH, NB;
+  if (conv_tile_geometry(a.H, a.W, &RH, &NB) != 0) return 0;
+  const int HW = a.H * a.W;
+  if (NB == 1) return ((a.H + RH - 1) / RH) * 4;
+  if (HW % 32 == 0 && NB * HW == 128) return HW / 32;
+  return 0;
+}
+
 // Pair tiles (256 pixels x <=256 channels) of the problem: a launch that cannot occupy even half of the 74 CTA pairs is
 // better served by the single-CTA kernel's narrower tiles (shorter critical path per tile).
 int conv_pair_tiles(const ConvGemmArgs& a) {
@@ -787,6 +811,7 @@ int conv_pair_launch(const ConvGemmArgs& a, cudaStream_t stream) {
   p.beta = a.beta; p.mod = a.mod; p.mod_stride = a.mod_stride;
   p.drop_p = a.drop_p; p.seed_lo = (uint32_t)a.seed; p.seed_hi = (uint32_t)(a.seed >> 32); p.seed_ptr = a.seed_ptr;
   p.aux = a.aux; p.d_mod = a.d_mod; p.nrm = a.nrm; p.accumulate_out = a.accumulate_out;
+  p.col_partial = (a.epi == EPI_PLAIN || a.epi == EPI_AXPBY) ? a.col_partial : nullptr;
   p.split_c = a.epi == EPI_SILU_BWD ? a.split_c : 0;
   if (p.split_c > 0)
     TEDM_CHECK(p.split_c % 64 == 0 && p.split_c < a.Cout && a.out2 != nullptr && a.mod != nullptr && a.d_mod != nullptr &&

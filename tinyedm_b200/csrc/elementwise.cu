@@ -737,6 +737,29 @@ bias_add_bc_kernel(__nv_bfloat16* __restrict__ g, const float* __restrict__ bias
 }
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(256)
+colsum_mean_kernel(const float* __restrict__ partial, float* __restrict__ mean, int slots, int C, float scale) {
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float* p0 = partial + (size_t)b * slots * C + c;
+  float t = 0.f;
+  for (int s = 0; s < slots; ++s) t += p0[(size_t)s * C];     // fixed order: bit-reproducible
+  mean[(size_t)b * C + c] = t * scale;
+}
+}  // namespace
+
+int colsum_mean(const float* partial, float* mean, int B, int slots, int C, float scale, cudaStream_t stream) {
+  if (B <= 0 || C <= 0) return 0;
+  TEDM_CHECK(slots > 0, "colsum_mean: no partial sums (slots = %d)", slots);
+  launch_pdl(colsum_mean_kernel, dim3((C + 255) / 256, B), 256, 0, stream, partial, mean, slots, C, scale);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+
 int bias_add_bc(__nv_bfloat16* g, const float* bias, float scale, int B, int HW, int C, cudaStream_t stream) {
   TEDM_CHECK(C % 8 == 0 && C > 0, "bias_add_bc: C must be a multiple of 8 (got %d)", C);
   const long long nvec = (long long)B * HW * (C / 8);

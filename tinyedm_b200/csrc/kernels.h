@@ -48,6 +48,10 @@ struct ConvGemmArgs {
   // channels >= split_c are multiplied by gain = mod[b, c - split_c] and go to `out2` ((B,H,W,C2)), and
   // d_mod[b, c - split_c] += sum_pixels g * x (= d gain * gain, because x holds skip * gain). 0 = off.
   int split_c;
+  // PLAIN / AXPBY, CTA-pair kernel only: per-warp column sums of the (bf16-rounded) output, written without atomics to
+  // col_partial[(m_tile * 4 + warp quarter)][Cout] (fp32); conv_colsum_slots() consecutive rows belong to one image, so
+  // ScaleLong's spatial mean of a skip tensor (networks.py:112) needs no extra pass over it. null = off.
+  float* col_partial;
 };
 
 // Device-side parameter block of the implicit-GEMM kernel.
@@ -73,14 +77,19 @@ struct ConvGemmParams {
   // tiles (two consecutive items = the two 128-channel halves of one pair tile); split_from == work_items: no split
   int split_from, work_items;
   int split_c;   // see ConvGemmArgs::split_c
+  float* col_partial;   // see ConvGemmArgs::col_partial
 };
 
 int conv_tile_geometry(int H, int W, int* RH, int* NB);
 int conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t stream);
-bool conv_split_supported(const ConvGemmArgs& a);   // ConvGemmArgs::split_c > 0 can be honoured (CTA-pair kernel)
+bool conv_split_supported(const ConvGemmArgs& a);
+// rows of col_partial per image if this launch takes the CTA-pair kernel and its tile geometry allows the sums, else 0
+int conv_colsum_slots(const ConvGemmArgs& a);
+int colsum_mean(const float* partial, float* mean, int B, int slots, int C, float scale, cudaStream_t stream);   // ConvGemmArgs::split_c > 0 can be honoured (CTA-pair kernel)
 // conv_pair.cu: the CTA-pair (tcgen05 cta_group::2) version with the TMA-staged epilogue
 bool conv_pair_supported(const ConvGemmArgs& a);
 int conv_pair_tiles(const ConvGemmArgs& a);
+int conv_pair_colsum_slots(const ConvGemmArgs& a);
 int conv_pair_launch(const ConvGemmArgs& a, cudaStream_t stream);
 
 struct ConvWgradArgs {

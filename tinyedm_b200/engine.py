@@ -252,6 +252,11 @@ class BlockPlan:
     gain: torch.nn.Parameter | None = None
 
 
+def fused_skip_mean_enabled() -> bool:
+    """TEDM_FUSED_SKIP_MEAN=0: ScaleLong's mean always through channel_dot (A/B switch)."""
+    return os.environ.get("TEDM_FUSED_SKIP_MEAN", "1") != "0"
+
+
 def split_epilogue_enabled() -> bool:
     """TEDM_SPLIT_EPILOGUE=0 keeps the separate concat-split / gain-gradient kernels in the backward (A/B switch)."""
     return os.environ.get("TEDM_SPLIT_EPILOGUE", "1") != "0"
@@ -408,27 +413,31 @@ class DenoiserEngine:
         # ---- input block (networks.py:578-587) ----
         xcol = ops.conv_in_im2col(noisy, sigma, float(m.sigma_data))
         C0 = m.encoder_out_channels[0]
-        x = ops.conv2d(xcol, self.s_in.fwd, 1, C0)
+        used = self._skips_consumed()
+        # ScaleLong's per-(image, channel) mean of a skip tensor (networks.py:112) comes out of the epilogue of the conv that
+        # produces the tensor (fixed-order partial sums, no atomics) when that launch runs on the CTA-pair kernel; otherwise
+        # it is reduced by channel_dot right after the tensor exists, while it is still (partly) in L2
+        x, mean0 = self._conv_with_mean(xcol, self.s_in.fwd, 1, C0, used[0])
         if taps is not None:
             taps["conv_in"] = x
         ctx = None
         if save:
             ctx = dict(B=B, H=H, W=W, noisy=noisy, sigma=sigma, emb=emb, lin=lin, mod=mod, xcol=xcol, blocks=[],
                        drop_p=drop_p, Be=Be)
-        # ScaleLong's per-(image, channel) mean of a skip tensor (networks.py:112) is taken as soon as the tensor exists,
-        # while the producing kernel's output is still (partly) in L2, not when the decoder pops it much later
-        used = self._skips_consumed()
         skips = [x]
-        means = [self._skip_mean(x) if used[0] else None]
+        means = [mean0]
+        n_pushed = 1
         for bp in self.blocks:
             skip = mean = None
             if bp.kind == "dec" and bp.cskip > 0:
                 skip = skips.pop()
                 mean = means.pop()
-            x, saved = self._block_forward(bp, x, skip, mod, mod_stride, drop_p, save, mean)
+            want_mean = bp.kind == "enc" and used[n_pushed]
+            x, saved, out_mean = self._block_forward(bp, x, skip, mod, mod_stride, drop_p, save, mean, want_mean)
             if bp.kind == "enc":
                 skips.append(x)
-                means.append(self._skip_mean(x) if used[len(skips) - 1] else None)
+                means.append(out_mean)
+                n_pushed += 1
             if save:
                 ctx["blocks"].append(saved)
             if taps is not None:
@@ -454,6 +463,20 @@ class DenoiserEngine:
         return self._skip_used
 
     @staticmethod
+    def _conv_with_mean(x: Tensor, w: Tensor, ksize: int, cout: int, want_mean: bool, **kw):
+        """conv2d (epilogue PLAIN or AXPBY) that also returns the spatial mean of its output per (image, channel)."""
+        if not want_mean:
+            return ops.conv2d(x, w, ksize, cout, **kw), None
+        B, H, W, cin = x.shape
+        slots = ops.conv2d_colsum_slots(B, H, W, cin, cout, ksize, kw.get("epi", 0)) if fused_skip_mean_enabled() else 0
+        if slots == 0:
+            out = ops.conv2d(x, w, ksize, cout, **kw)
+            return out, DenoiserEngine._skip_mean(out)
+        part = torch.empty((B * slots, cout), device=x.device, dtype=F32)
+        out = ops.conv2d(x, w, ksize, cout, col_partial=part, **kw)
+        return out, ops.colsum_mean(part, B, slots, cout, 1.0 / (H * W))
+
+    @staticmethod
     def _skip_mean(x: Tensor) -> Tensor:
         B, H, W, C = x.shape
         mean = torch.zeros((B, C), device=x.device, dtype=F32)
@@ -461,7 +484,8 @@ class DenoiserEngine:
         return mean
 
     def _block_forward(self, bp: BlockPlan, xin: Tensor, skip: Tensor | None, mod: Tensor, mod_stride: int,
-                       drop_p: float, save: bool, skip_mean: Tensor | None = None):
+                       drop_p: float, save: bool, skip_mean: Tensor | None = None, want_mean: bool = False):
+        """Returns (block output, tensors saved for backward, spatial mean of the output per (image, channel) or None)."""
         S: dict = {}
         B, Hin, Win, _ = xin.shape
         S["in_shape"] = (B, Hin, Win)
@@ -494,18 +518,20 @@ class DenoiserEngine:
         raw = torch.empty((x.shape[0], x.shape[1], x.shape[2], bp.cout), device=x.device, dtype=BF16) if save else None
         h = ops.conv2d(a, bp.w["conv_3x3_1"].fwd, 3, bp.cout, epi=EPI_MODSILU, mod=mod, mod_off=bp.col0,
                        mod_stride=mod_stride, drop_p=drop_p, seed=0x5EED0000 + bp.index, seed_ptr=self.step_counter, raw=raw)
-        out = ops.conv2d(h, bp.w["conv_3x3_2"].fwd, 3, bp.cout, epi=EPI_AXPBY, alpha=wb, beta=wa, res=xr)
+        out, out_mean = self._conv_with_mean(h, bp.w["conv_3x3_2"].fwd, 3, bp.cout, want_mean and not bp.attn, epi=EPI_AXPBY,
+                                             alpha=wb, beta=wa, res=xr)
         if save:
             S.update(x=x, a=a, raw=raw, h=h)
         if bp.attn:
             c5 = 1.0 / math.sqrt(2.0)
             qkv = ops.conv2d(out, bp.w["qkv"].fwd, 1, 3 * bp.cout)
             y, lse = ops.attention_forward(qkv, self.m.num_heads, need_lse=save)
-            out2 = ops.conv2d(y, bp.w["out"].fwd, 1, bp.cout, epi=EPI_AXPBY, alpha=c5, beta=c5, res=out)
+            out2, out_mean = self._conv_with_mean(y, bp.w["out"].fwd, 1, bp.cout, want_mean, epi=EPI_AXPBY, alpha=c5, beta=c5,
+                                                  res=out)
             if save:
                 S.update(mid=out, qkv=qkv, lse=lse, y=y)
             out = out2
-        return out, S
+        return out, S, out_mean
 
     # =====================================================================================================
     # backward

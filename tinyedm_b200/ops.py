@@ -68,7 +68,7 @@ def conv2d(x: Tensor, w: Tensor, ksize: int, cout: int, *, epi: int = EPI_PLAIN,
            res: Tensor | None = None, raw: Tensor | None = None, mod: Tensor | None = None, mod_off: int = 0,
            mod_stride: int | None = None, drop_p: float = 0.0, seed: int = 0, seed_ptr: Tensor | None = None,
            out: Tensor | None = None, block_n: int = 0, aux: Tensor | None = None, d_mod: Tensor | None = None,
-           nrm: Tensor | None = None, accumulate_out: bool = False) -> Tensor:
+           nrm: Tensor | None = None, accumulate_out: bool = False, col_partial: Tensor | None = None) -> Tensor:
     """Implicit-GEMM MPConv (forward or data gradient). `w` is the prepared bf16 weight [cout][k*k][cin]."""
     B, H, W, cin = x.shape
     if out is None:
@@ -81,8 +81,19 @@ def conv2d(x: Tensor, w: Tensor, ksize: int, cout: int, *, epi: int = EPI_PLAIN,
     d_mod_ptr = None if d_mod is None else d_mod.data_ptr() + 4 * mod_off
     _lib.call("tedm_conv2d_forward", x.data_ptr(), w.data_ptr(), out.data_ptr(), B, H, W, cin, cout, ksize, epi, alpha,
               _p(raw), _p(res), beta, mod_ptr, mod_stride or 0, drop_p, seed, _p(seed_ptr), block_n, _p(aux), d_mod_ptr,
-              _p(nrm), 1 if accumulate_out else 0, _stream())
+              _p(nrm), 1 if accumulate_out else 0, _p(col_partial), _stream())
     return out
+
+
+def conv2d_colsum_slots(B: int, H: int, W: int, cin: int, cout: int, ksize: int, epi: int) -> int:
+    """Rows per image of the `col_partial` output of `conv2d` for this launch (0: not available, reduce with channel_dot)."""
+    return _lib.call_int("tedm_conv2d_colsum_slots", B, H, W, cin, cout, ksize, epi)
+
+
+def colsum_mean(col_partial: Tensor, B: int, slots: int, C: int, scale: float) -> Tensor:
+    mean = torch.empty((B, C), device=col_partial.device, dtype=F32)
+    _lib.call("tedm_colsum_mean", col_partial.data_ptr(), mean.data_ptr(), B, slots, C, scale, _stream())
+    return mean
 
 
 def conv2d_dgrad_split_supported(B: int, H: int, W: int, cin: int, c1: int, c2: int, ksize: int) -> bool:
