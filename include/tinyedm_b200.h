@@ -64,12 +64,14 @@ int tedm_weight_prep_backward(const tedm_weight_desc* table, int n, int total_ro
  *             d_mod[b,c] += sum_pixels (needs aux = raw, mod, d_mod zeroed by the caller, the same seed/seed_ptr)
  *           4 adjoint of a = mp_silu(x) fused into the dgrad of conv_3x3_1: out = conv*mp_silu'(aux=x) + beta*res,
  *             then, when nrm (eps + rms per pixel, from tedm_block_prep_forward) is given, the pixel_norm adjoint
- *             g/n - x*sum_c(g*x)/((n-eps)*C) (needs Cout <= 256), then out += previous out when accumulate_out   */
+ *             g/n - x*sum_c(g*x)/((n-eps)*C) (needs Cout <= 256), then out += previous out when accumulate_out,
+ *             then out[b,p,c] += out_bias_scale * out_bias[b,c] when out_bias (fp32 (B,Cout)) is given: a pending
+ *             per-(image, channel) share of the same gradient, e.g. ScaleLong's mean gradient (networks.py:112)  */
 int tedm_conv2d_forward(const void* x, const void* w, void* out, int B, int H, int W, int Cin, int Cout, int ksize,
                         int epilogue, float alpha, void* raw, const void* res, float beta, const float* mod,
                         int mod_stride, float drop_p, uint64_t seed, const uint64_t* seed_ptr, int block_n,
                         const void* aux, float* d_mod, const float* nrm, int accumulate_out, float* col_partial,
-                        tedm_stream_t stream);
+                        const float* out_bias, float out_bias_scale, tedm_stream_t stream);
 /* Epilogues 0 and 2 can also emit per-(image, channel) partial sums of the stored output, so that ScaleLong's spatial
  * mean of a skip tensor (networks.py:112) needs no pass over the tensor: col_partial is fp32 [B * slots][Cout] with
  * slots = tedm_conv2d_colsum_slots(...) rows per image (0: not available for this launch - pass NULL and reduce the tensor
@@ -85,11 +87,12 @@ int tedm_colsum_mean(const float* col_partial, float* mean, int B, int slots, in
  *                                                                tedm_bias_add_bc once d gain is known)
  *   d_gx  (B,C2)      +=  sum_pixels g_cat[..., C1:] * x[..., C1:]   = d gain * gain (x holds skip*gain); zero it first
  * g: gradient w.r.t. the conv output (B,H,W,Cin); w: the out_dgrad weight layout [C1+C2][k*k][Cin]; x, res: (B,H,W,C1+C2).
+ * in_bias (fp32 (B,C1), may be NULL): g_in[b,p,c] += in_bias_scale * in_bias[b,c], as out_bias of tedm_conv2d_forward.
  * Only the CTA-pair kernel implements it: ask tedm_conv2d_dgrad_split_supported (returns 1 / 0) first. */
 int tedm_conv2d_dgrad_split_supported(int B, int H, int W, int Cin, int C1, int C2, int ksize);
 int tedm_conv2d_dgrad_split(const void* g, const void* w, void* g_in, void* g_skip, int B, int H, int W, int Cin, int C1,
                             int C2, int ksize, float alpha, const void* x, const void* res, float beta, const float* gain,
-                            float* d_gx, int accumulate_in, tedm_stream_t stream);
+                            float* d_gx, int accumulate_in, const float* in_bias, float in_bias_scale, tedm_stream_t stream);
 /* g[b,p,c] += scale * bias[b,c]  (bf16 NHWC tensor, fp32 per-(image, channel) bias): the gradient of ScaleLong's
  * spatial mean (networks.py:112) with scale = 1/HW */
 int tedm_bias_add_bc(void* g, const float* bias, float scale, int B, int HW, int C, tedm_stream_t stream);

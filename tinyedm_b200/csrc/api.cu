@@ -25,7 +25,7 @@ int tedm_conv2d_forward(const void* x, const void* w, void* out, int B, int H, i
                         int epilogue, float alpha, void* raw, const void* res, float beta, const float* mod,
                         int mod_stride, float drop_p, uint64_t seed, const uint64_t* seed_ptr, int block_n,
                         const void* aux, float* d_mod, const float* nrm, int accumulate_out, float* col_partial,
-                        tedm_stream_t stream) {
+                        const float* out_bias, float out_bias_scale, tedm_stream_t stream) {
   ConvGemmArgs a{};
   a.x = static_cast<const __nv_bfloat16*>(x);
   a.w = static_cast<const __nv_bfloat16*>(w);
@@ -41,6 +41,7 @@ int tedm_conv2d_forward(const void* x, const void* w, void* out, int B, int H, i
   a.aux = static_cast<const __nv_bfloat16*>(aux);
   a.d_mod = d_mod; a.nrm = nrm; a.accumulate_out = accumulate_out;
   a.col_partial = col_partial;
+  a.out_bias = out_bias; a.out_bias_scale = out_bias_scale;
   return conv_gemm_launch(a, static_cast<cudaStream_t>(stream));
 }
 int tedm_conv2d_colsum_slots(int B, int H, int W, int Cin, int Cout, int ksize, int epilogue) {
@@ -65,7 +66,7 @@ int tedm_conv2d_dgrad_split_supported(int B, int H, int W, int Cin, int C1, int 
 }
 int tedm_conv2d_dgrad_split(const void* g, const void* w, void* g_in, void* g_skip, int B, int H, int W, int Cin, int C1,
                             int C2, int ksize, float alpha, const void* x, const void* res, float beta, const float* gain,
-                            float* d_gx, int accumulate_in, tedm_stream_t stream) {
+                            float* d_gx, int accumulate_in, const float* in_bias, float in_bias_scale, tedm_stream_t stream) {
   ConvGemmArgs a = dgrad_split_args(B, H, W, Cin, C1, C2, ksize);
   a.x = static_cast<const __nv_bfloat16*>(g);
   a.w = static_cast<const __nv_bfloat16*>(w);
@@ -77,6 +78,7 @@ int tedm_conv2d_dgrad_split(const void* g, const void* w, void* g_in, void* g_sk
   a.beta = beta;
   a.mod = gain; a.mod_stride = C2; a.d_mod = d_gx;
   a.accumulate_out = accumulate_in;
+  a.out_bias = in_bias; a.out_bias_scale = in_bias_scale;
   return conv_gemm_launch(a, static_cast<cudaStream_t>(stream));
 }
 int tedm_bias_add_bc(void* g, const float* bias, float scale, int B, int HW, int C, tedm_stream_t stream) {

@@ -409,6 +409,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
               for (int i = 0; i < CW; ++i) v[i] += ov[i];
             }
+            if (p.out_bias != nullptr) {
+              const float* brow = p.out_bias + (long long)b * p.Cout + t.n0 + c0;
+#pragma unroll
+              for (int i = 0; i < CW; ++i)
+                if (c0 + i < n_this) v[i] = fmaf(p.out_bias_scale, brow[i], v[i]);
+            }
           }
           row_store<CW>(out_row + c0, v, n_this - c0);
         }
@@ -552,6 +558,7 @@ int conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t stream) {
   p.beta = a.beta; p.mod = a.mod; p.mod_stride = a.mod_stride;
   p.drop_p = a.drop_p; p.seed_lo = (uint32_t)a.seed; p.seed_hi = (uint32_t)(a.seed >> 32); p.seed_ptr = a.seed_ptr;
   p.aux = a.aux; p.d_mod = a.d_mod; p.nrm = a.nrm; p.accumulate_out = a.accumulate_out;
+  p.out_bias = a.epi == EPI_SILU_BWD ? a.out_bias : nullptr; p.out_bias_scale = a.out_bias_scale;
   if (a.epi == EPI_MODSILU) TEDM_CHECK(a.mod != nullptr, "conv_gemm: MODSILU epilogue needs mod");
   if (a.epi == EPI_AXPBY) TEDM_CHECK(a.res != nullptr, "conv_gemm: AXPBY epilogue needs res");
   if (a.epi == EPI_MODSILU_BWD)

@@ -579,6 +579,18 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                 for (int i = 0; i < CW; ++i) v[i] += ov[i];
               }
+              if (p.out_bias != nullptr && valid) {
+                const int cb_ = p.split_c > 0 ? p.split_c : p.Cout;     // channels of `out`
+                const float* brow = p.out_bias + (long long)b * cb_ + n0 + cc;
+#pragma unroll
+                for (int g = 0; g < CW / 4; ++g) {
+                  const float4 bb = *reinterpret_cast<const float4*>(brow + g * 4);
+                  v[g * 4 + 0] = fmaf(p.out_bias_scale, bb.x, v[g * 4 + 0]);
+                  v[g * 4 + 1] = fmaf(p.out_bias_scale, bb.y, v[g * 4 + 1]);
+                  v[g * 4 + 2] = fmaf(p.out_bias_scale, bb.z, v[g * 4 + 2]);
+                  v[g * 4 + 3] = fmaf(p.out_bias_scale, bb.w, v[g * 4 + 3]);
+                }
+              }
               srow_store<CW>(buf2, m, j0, v);
             }
           }
@@ -812,6 +824,7 @@ int conv_pair_launch(const ConvGemmArgs& a, cudaStream_t stream) {
   p.drop_p = a.drop_p; p.seed_lo = (uint32_t)a.seed; p.seed_hi = (uint32_t)(a.seed >> 32); p.seed_ptr = a.seed_ptr;
   p.aux = a.aux; p.d_mod = a.d_mod; p.nrm = a.nrm; p.accumulate_out = a.accumulate_out;
   p.col_partial = (a.epi == EPI_PLAIN || a.epi == EPI_AXPBY) ? a.col_partial : nullptr;
+  p.out_bias = a.epi == EPI_SILU_BWD ? a.out_bias : nullptr; p.out_bias_scale = a.out_bias_scale;
   p.split_c = a.epi == EPI_SILU_BWD ? a.split_c : 0;
   if (p.split_c > 0)
     TEDM_CHECK(p.split_c % 64 == 0 && p.split_c < a.Cout && a.out2 != nullptr && a.mod != nullptr && a.d_mod != nullptr &&

@@ -52,6 +52,10 @@ struct ConvGemmArgs {
   // col_partial[(m_tile * 4 + warp quarter)][Cout] (fp32); conv_colsum_slots() consecutive rows belong to one image, so
   // ScaleLong's spatial mean of a skip tensor (networks.py:112) needs no extra pass over it. null = off.
   float* col_partial;
+  // SILU_BWD: out[b,p,c] += out_bias_scale * out_bias[b,c] (fp32 (B, channels of `out`)): a pending per-(image, channel)
+  // gradient share - ScaleLong's mean gradient - folded into the kernel that accumulates into the tensor anyway. null = off.
+  const float* out_bias;
+  float out_bias_scale;
 };
 
 // Device-side parameter block of the implicit-GEMM kernel.
@@ -78,6 +82,8 @@ struct ConvGemmParams {
   int split_from, work_items;
   int split_c;   // see ConvGemmArgs::split_c
   float* col_partial;   // see ConvGemmArgs::col_partial
+  const float* out_bias;   // see ConvGemmArgs::out_bias
+  float out_bias_scale;
 };
 
 int conv_tile_geometry(int H, int W, int* RH, int* NB);

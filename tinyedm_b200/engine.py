@@ -579,7 +579,7 @@ class DenoiserEngine:
         g = ops.conv_out_backward(g_D, ctx["f_raw"], ctx["x_last"], self.s_out.fwd, m.gain_out, sigma,
                                   float(m.sigma_data), self.s_out.ghat, sg[nb:])
         d_mod = torch.zeros((B, self.n_mod), device=dev, dtype=F32)
-        pending: dict[int, Tensor] = {}
+        pending: dict[int, tuple] = {}   # skip index -> (g_skip, pending per-(image, channel) share or None, its scale)
         for bp, S in zip(reversed(self.blocks), reversed(ctx["blocks"])):
             g = self._block_backward(bp, S, g, ctx, d_mod, pending)
             if sync is not None:
@@ -609,9 +609,19 @@ class DenoiserEngine:
     def _take_g_in(self, bp: BlockPlan, pending: dict, shape, dev):
         """Buffer receiving the gradient w.r.t. this block's input. If the input is also a skip source whose
         decoder already deposited its share, accumulate into that buffer."""
+        g, acc, bias, scale = self._take_g_in_bias(bp, pending, shape, dev)
+        if bias is not None:
+            ops.bias_add_bc(g, bias, scale)      # this consumer's kernel cannot fold the per-(image, channel) share in
+        return g, acc
+
+    def _take_g_in_bias(self, bp: BlockPlan, pending: dict, shape, dev):
+        """As `_take_g_in`, for consumers whose kernel adds a pending per-(image, channel) share itself (`out_bias` of the
+        SILU_BWD conv epilogue): returns (buffer, accumulate, bias or None, bias scale). The share is the gradient through
+        ScaleLong's spatial mean, deposited with the decoder's g_skip instead of being added by a pass of its own."""
         if bp.in_src >= 0 and bp.in_src in pending:
-            return pending.pop(bp.in_src), True
-        return torch.empty(shape, device=dev, dtype=BF16), False
+            g, bias, scale = pending.pop(bp.in_src)
+            return g, True, bias, scale
+        return torch.empty(shape, device=dev, dtype=BF16), False, None, 1.0
 
     def _attn_backward(self, bp: BlockPlan, S: dict, g_out: Tensor) -> Tensor:
         c5 = 1.0 / math.sqrt(2.0)
@@ -642,9 +652,9 @@ class DenoiserEngine:
             fuse_pn = bp.cout <= 256          # the fused pixel-norm adjoint needs all channels in one N tile
             if fuse_pn and not has_1x1 and bp.resample == RESAMPLE_NONE:
                 # conv1's data gradient, mp_silu', the residual share and the pixel-norm adjoint in ONE kernel
-                g_in, acc = self._take_g_in(bp, pending, (B, Hin, Win, bp.cin), dev)
+                g_in, acc, bias, bscale = self._take_g_in_bias(bp, pending, (B, Hin, Win, bp.cin), dev)
                 ops.conv2d(g_raw, w1.dgrad, 3, bp.cout, epi=EPI_SILU_BWD, aux=x, res=g_mid, beta=wa, nrm=S["nrm"], out=g_in,
-                           accumulate_out=acc)
+                           accumulate_out=acc, out_bias=bias, out_bias_scale=bscale)
                 return g_in
             if fuse_pn:
                 g_u = ops.conv2d(g_raw, w1.dgrad, 3, bp.cout, epi=EPI_SILU_BWD, aux=x, res=g_mid, beta=wa, nrm=S["nrm"])
@@ -675,24 +685,26 @@ class DenoiserEngine:
         else:
             g_res, beta = g_mid, wa
         if bp.cskip == 0 and bp.resample == RESAMPLE_NONE:
-            g_in, acc = self._take_g_in(bp, pending, (B, Hin, Win, bp.cin), dev)
-            ops.conv2d(g_raw, w1.dgrad, 3, ctot, epi=EPI_SILU_BWD, aux=x, res=g_res, beta=beta, out=g_in, accumulate_out=acc)
+            g_in, acc, bias, bscale = self._take_g_in_bias(bp, pending, (B, Hin, Win, bp.cin), dev)
+            ops.conv2d(g_raw, w1.dgrad, 3, ctot, epi=EPI_SILU_BWD, aux=x, res=g_res, beta=beta, out=g_in, accumulate_out=acc,
+                       out_bias=bias, out_bias_scale=bscale)
             return g_in
         if (bp.cskip > 0 and bp.resample == RESAMPLE_NONE and split_epilogue_enabled()
                 and ops.conv2d_dgrad_split_supported(B, Hin, Win, bp.cout, bp.cin, bp.cskip, 3)):
             # conv1's data gradient, mp_silu', the residual share, the concat split, the ScaleLong gain and the reduction
             # for d(gain) in ONE kernel: g_cat is never materialised (it used to be written once and read twice)
             Cs = bp.cskip
-            g_in, acc = self._take_g_in(bp, pending, (B, Hin, Win, bp.cin), dev)
+            g_in, acc, bias, bscale = self._take_g_in_bias(bp, pending, (B, Hin, Win, bp.cin), dev)
             g_skip = torch.empty((B, Hin, Win, Cs), device=dev, dtype=BF16)
             d_gx = torch.zeros((B, Cs), device=dev, dtype=F32)
             ops.conv2d_dgrad_split(g_raw, w1.dgrad, 3, x=x, res=g_res, beta=beta, gain=S["gain"], g_in=g_in, g_skip=g_skip,
-                                   d_gx=d_gx, accumulate_in=acc)
+                                   d_gx=d_gx, accumulate_in=acc, in_bias=bias, in_bias_scale=bscale)
             s1, s2 = bp.w["sl1"], bp.w["sl2"]
             d_pre2, d_hpre, d_mean = ops.scalelong_backward(d_gx, S["gain"], S["h_pre"], s1.f32, s2.f32, d_gain_times_gain=True)
             ops.scalelong_wgrad(d_pre2, S["hh"], d_hpre, S["aug"], s2.ghat, s1.ghat)   # into the zeroed g_hat buffer
-            ops.bias_add_bc(g_skip, d_mean, 1.0 / (Hin * Win))    # gradient through the spatial mean of [skip, 1]
-            pending[bp.skip_src] = g_skip
+            # the gradient through the spatial mean of [skip, 1] (d_mean / HW on every pixel) travels with g_skip and is
+            # added by the kernel that accumulates the encoder side's gradient into it
+            pending[bp.skip_src] = (g_skip, d_mean, 1.0 / (Hin * Win))
             return g_in
         # gradient w.r.t. x on the post-resample grid: conv1's data gradient * mp_silu'(x) + the residual share
         g_x = ops.conv2d(g_raw, w1.dgrad, 3, ctot, epi=EPI_SILU_BWD, aux=x, res=g_res, beta=beta)
@@ -721,7 +733,7 @@ class DenoiserEngine:
         ops.block_prep_backward(g_res=g_cat, beta=1.0, g_a=None, x=None, nrm=None, gain=S["gain"], d_mean=d_mean,
                                 g_in=g_in, g_skip=g_skip, accumulate_in=acc, accumulate_skip=False, B=B, Hin=Hin, Win=Win,
                                 C1=bp.cin, C2=Cs, resample=RESAMPLE_NONE, pixelnorm=False)
-        pending[bp.skip_src] = g_skip
+        pending[bp.skip_src] = (g_skip, None, 1.0)
         return g_in
 
     # ---- parameter / gradient enumeration in `module.parameters()` order ----

@@ -68,7 +68,8 @@ def conv2d(x: Tensor, w: Tensor, ksize: int, cout: int, *, epi: int = EPI_PLAIN,
            res: Tensor | None = None, raw: Tensor | None = None, mod: Tensor | None = None, mod_off: int = 0,
            mod_stride: int | None = None, drop_p: float = 0.0, seed: int = 0, seed_ptr: Tensor | None = None,
            out: Tensor | None = None, block_n: int = 0, aux: Tensor | None = None, d_mod: Tensor | None = None,
-           nrm: Tensor | None = None, accumulate_out: bool = False, col_partial: Tensor | None = None) -> Tensor:
+           nrm: Tensor | None = None, accumulate_out: bool = False, col_partial: Tensor | None = None,
+           out_bias: Tensor | None = None, out_bias_scale: float = 1.0) -> Tensor:
     """Implicit-GEMM MPConv (forward or data gradient). `w` is the prepared bf16 weight [cout][k*k][cin]."""
     B, H, W, cin = x.shape
     if out is None:
@@ -81,7 +82,7 @@ def conv2d(x: Tensor, w: Tensor, ksize: int, cout: int, *, epi: int = EPI_PLAIN,
     d_mod_ptr = None if d_mod is None else d_mod.data_ptr() + 4 * mod_off
     _lib.call("tedm_conv2d_forward", x.data_ptr(), w.data_ptr(), out.data_ptr(), B, H, W, cin, cout, ksize, epi, alpha,
               _p(raw), _p(res), beta, mod_ptr, mod_stride or 0, drop_p, seed, _p(seed_ptr), block_n, _p(aux), d_mod_ptr,
-              _p(nrm), 1 if accumulate_out else 0, _p(col_partial), _stream())
+              _p(nrm), 1 if accumulate_out else 0, _p(col_partial), _p(out_bias), out_bias_scale, _stream())
     return out
 
 
@@ -101,14 +102,15 @@ def conv2d_dgrad_split_supported(B: int, H: int, W: int, cin: int, c1: int, c2: 
 
 
 def conv2d_dgrad_split(g: Tensor, w: Tensor, ksize: int, *, x: Tensor, res: Tensor, beta: float, gain: Tensor, g_in: Tensor,
-                       g_skip: Tensor, d_gx: Tensor, accumulate_in: bool, alpha: float = 1.0) -> None:
+                       g_skip: Tensor, d_gx: Tensor, accumulate_in: bool, alpha: float = 1.0, in_bias: Tensor | None = None,
+                       in_bias_scale: float = 1.0) -> None:
     """Data gradient of a skip-decoder block's first conv with the concat split, the ScaleLong gain and the reduction for
     d(gain) fused into the epilogue (see tedm_conv2d_dgrad_split). d_gx (B,C2) fp32 must be zeroed by the caller."""
     B, H, W, cin = g.shape
     c1, c2 = g_in.shape[3], g_skip.shape[3]
     _lib.call("tedm_conv2d_dgrad_split", g.data_ptr(), w.data_ptr(), g_in.data_ptr(), g_skip.data_ptr(), B, H, W, cin, c1, c2,
               ksize, alpha, x.data_ptr(), res.data_ptr(), beta, gain.data_ptr(), d_gx.data_ptr(), 1 if accumulate_in else 0,
-              _stream())
+              _p(in_bias), in_bias_scale, _stream())
 
 
 def bias_add_bc(g: Tensor, bias: Tensor, scale: float) -> None:
