@@ -18,8 +18,9 @@ except Exception:
     PEAK = 6551.7
 flush_buf = torch.empty(256 << 20, device=dev, dtype=torch.uint8)   # > L2 (126 MB)
 
-def bench(fn, n=10):
-    for _ in range(2):
+ITERS = int(os.environ.get("EW_ITERS", 10))   # EW_ITERS=1 under ncu: one cold launch per case
+def bench(fn, n=ITERS):
+    for _ in range(2 if n > 1 else 0):
         fn()
     ts = []
     for _ in range(n):
