@@ -34,7 +34,7 @@ typedef struct tedm_weight_desc {
   void* out_fwd;     /* bf16 w_hat [rows][kpad], k = tap*cin + ci (zero padded)   or NULL      */
   void* out_dgrad;   /* bf16 w_hat [cin][taps flipped][rows]                      or NULL      */
   void* out_f32;     /* fp32 w_hat [rows][cin*taps]                               or NULL      */
-  void* stats;       /* fp32 [rows][2] = {1/(eps*sqrt(n)+||w||), ||w||}                        */
+  void* stats;       /* fp32 [rows][4] = {1/(eps*sqrt(n)+||w||), ||w||, training rescale, 0}; required, 16-byte aligned */
   int32_t rows, cin, taps, kpad, row_start;
   int32_t qkv_head_dim; /* != 0: qkv conv of CosineAttention — prepared rows are permuted from the reference's
                            head*3*hd + d*3 + {q,k,v} (networks.py:194) to {q,k,v}*C + head*hd + d, so the conv emits
@@ -46,7 +46,7 @@ typedef struct tedm_weight_desc {
  * training != 0 additionally rewrites every parameter in place: w <- normalize(w)  (networks.py:32-34). */
 int tedm_weight_prep_forward(const tedm_weight_desc* table, int n, int total_groups, int training, tedm_stream_t stream);
 /* dL/dw = g/s - w (w.g)/(s^2 ||w||) for every descriptor with g_hat and grad set (autograd of :35-36).
- * total_rows = sum(rows); max_row_floats = max over descriptors of taps*(cin+1) (shared-memory staging of one row). */
+ * total_rows = sum(rows); max_row_floats = max over descriptors of taps*(cin+4) (shared-memory staging of one row). */
 int tedm_weight_prep_backward(const tedm_weight_desc* table, int n, int total_rows, int max_row_floats,
                               tedm_stream_t stream);
 

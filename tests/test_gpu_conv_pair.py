@@ -101,7 +101,13 @@ def test_pair_conv_epilogues_vs_torch(dev, B, H, W, Cin, Cout, ks):
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,ks", [(40, 32, 32, 256, 256, 3), (33, 16, 16, 512, 256, 3), (9, 16, 16, 256, 768, 1),
-                                               (70, 8, 8, 128, 256, 3), (5, 14, 14, 256, 256, 3), (3, 7, 7, 512, 512, 3)])
+                                               (70, 8, 8, 128, 256, 3), (5, 14, 14, 256, 256, 3), (3, 7, 7, 512, 512, 3),
+                                               # transposed pair kernel (k slabs on M, output channels on N): the ImageNet-latent
+                                               # and MNIST channel counts, N = 192 blocks, padded last N block, padded k slab
+                                               (3, 64, 64, 192, 192, 3), (5, 32, 32, 384, 384, 3), (4, 16, 16, 576, 576, 3),
+                                               (4, 32, 32, 576, 384, 3), (6, 16, 16, 576, 1728, 1), (2, 28, 28, 128, 128, 3),
+                                               (3, 16, 16, 1344, 768, 3), (2, 8, 8, 768, 576, 1), (9, 8, 8, 64, 128, 3),
+                                               (3, 16, 16, 128, 320, 3), (12, 64, 64, 192, 192, 3), (5, 7, 7, 128, 384, 3)])
 def test_pair_wgrad_vs_torch_and_single(dev, B, H, W, Cin, Cout, ks):
     from tinyedm_b200 import ops
     ops.ensure_device(dev)

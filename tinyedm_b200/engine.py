@@ -84,7 +84,7 @@ class WeightBank:
         self._have_grad_buffers = False
         self.total_rows = sum(s.rows for s in slots)
         self.total_groups = sum((s.rows + 15) // 16 for s in slots)     # 16 prepared rows per CTA of weight_prep_fwd
-        self.max_row_floats = max(s.taps * (s.cin + 1) for s in slots)  # staging of one dL/dw_hat row in weight_prep_bwd
+        self.max_row_floats = max(s.taps * (s.cin + 4) for s in slots)  # staging of one dL/dw_hat row in weight_prep_bwd
 
     # ---- buffers ----
     def materialise(self, device: torch.device) -> None:
@@ -106,7 +106,7 @@ class WeightBank:
         self._fwd_flat = torch.zeros(max(n_fwd, 1), device=device, dtype=BF16)
         self._dg_flat = torch.zeros(max(n_dg, 1), device=device, dtype=BF16)
         self._f32_flat = torch.zeros(max(n_f32, 1), device=device, dtype=F32)
-        self.stats = torch.zeros(2 * self.total_rows, device=device, dtype=F32)
+        self.stats = torch.zeros(4 * self.total_rows, device=device, dtype=F32)
         for s, (of, od, o3) in zip(self.slots, offs):
             n = s.rows * s.cin * s.taps
             if s.want_fwd:
@@ -183,7 +183,7 @@ class WeightBank:
             d.out_fwd = s.fwd.data_ptr() if s.fwd is not None else None
             d.out_dgrad = s.dgrad.data_ptr() if s.dgrad is not None else None
             d.out_f32 = s.f32.data_ptr() if s.f32 is not None else None
-            d.stats = self.stats.data_ptr() + 8 * s.row_start
+            d.stats = self.stats.data_ptr() + 16 * s.row_start
             d.rows, d.cin, d.taps, d.kpad, d.row_start = s.rows, s.cin, s.taps, s.kpad, s.row_start
             d.qkv_head_dim = s.qkv_head_dim
         self._table = self._upload(bytes(arr))
