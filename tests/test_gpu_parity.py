@@ -99,12 +99,18 @@ def test_conv_dgrad_is_the_adjoint(dev):
         assert rel(gx, gx_ref.permute(0, 2, 3, 1)) < 6e-3
 
 
-def test_weight_prep_forward_backward_and_forced_rewrite(dev):
+@pytest.mark.parametrize("shapes", [
+    [(64, 64, 3, 3), (128, 64, 1, 1), (16, 257, 1, 1), (96, 40)],
+    # long rows (ImageNet-latent decoder: 9 x 1536 floats): several fan-in tiles per 16-row group strided over blockIdx.y,
+    # the 256-thread backward with > 48 KB of staging, a row count that is not a multiple of 16
+    [(32, 1536, 3, 3), (40, 768, 3, 3), (24, 1000), (48, 320, 3, 3)],
+])
+def test_weight_prep_forward_backward_and_forced_rewrite(dev, shapes):
     from tinyedm_b200.engine import WeightBank, conv_slot, f32_slot
     torch.manual_seed(11)
-    shapes = [(64, 64, 3, 3), (128, 64, 1, 1), (16, 257, 1, 1), (96, 40)]
     params = [torch.nn.Parameter(torch.randn(*s, device=dev) * (0.5 + i)) for i, s in enumerate(shapes)]
-    slots = [conv_slot("a", params[0]), conv_slot("b", params[1]), f32_slot("c", params[2]), f32_slot("d", params[3])]
+    slots = [conv_slot("a", params[0]), conv_slot("b", params[1]), f32_slot("c", params[2]),
+             conv_slot("d", params[3]) if len(shapes[3]) == 4 else f32_slot("d", params[3])]
     bank = WeightBank(slots)
     bank.materialise(dev)
     before = [p.detach().cpu().clone() for p in params]
@@ -118,6 +124,9 @@ def test_weight_prep_forward_backward_and_forced_rewrite(dev):
         else:
             got = s.fwd.float().view(b.shape[0], b.shape[2], b.shape[3], b.shape[1]).permute(0, 3, 1, 2)
             assert rel(got, w_hat) < 3e-3
+            if s.dgrad is not None:   # data-gradient operand: [cin][tap flipped][rows]
+                got_d = s.dgrad.float().view(b.shape[1], b.shape[2], b.shape[3], b.shape[0])
+                assert rel(got_d, w_hat.flip(2, 3).permute(1, 2, 3, 0)) < 3e-3
     # backward through the normalisation vs autograd of the oracle
     bank.ensure_grad_buffers()
     bank.prepare(False)
@@ -133,7 +142,7 @@ def test_weight_prep_forward_backward_and_forced_rewrite(dev):
         if s.taps > 1:   # g_hat is [rows][tap][cin]
             g_oihw = g.view(s.rows, 3, 3, s.cin).permute(0, 3, 1, 2)
         else:
-            g_oihw = g.view_as(w_hat)
+            g_oihw = g[:, :w_hat[0].numel()].reshape(w_hat.shape)
         (gw,) = torch.autograd.grad(w_hat, w, g_oihw)
         assert rel(s.grad, gw) < 1e-5, s.name
     # training: in-place forced re-normalisation (networks.py:32-34)

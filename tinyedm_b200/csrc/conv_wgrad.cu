@@ -705,6 +705,7 @@ bool wgrad_pair_t_plan(const ConvWgradArgs& a, WgradTParams* p, int* splits) {
   if (p->stages * p->stage_bytes < (256 / 32) * 4 * 4096) return false;   // epilogue staging
   p->slabs_per_tap = a.Cin / 64;
   p->total_slabs = p->taps * p->slabs_per_tap;
+  if (p->total_slabs < 3) return false;   // a 1x1 conv over <= 128 channels would fill less than 3/4 of the 256 accumulator lanes
   p->m_blks = (p->total_slabs + 3) / 4;
   p->tiles_h = (a.H + p->RH - 1) / p->RH;
   p->p_tiles = ((a.B + p->NB - 1) / p->NB) * p->tiles_h;
