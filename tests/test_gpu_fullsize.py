@@ -22,13 +22,16 @@ def dev():
     return torch.device("cuda:0")
 
 
-@pytest.mark.parametrize("H,Cin,Cout,ks", [(32, 256, 256, 3), (16, 512, 256, 3), (16, 256, 768, 1), (8, 256, 256, 3)])
-def test_conv_triple_bilinear_identities_at_batch_256(dev, H, Cin, Cout, ks):
+# CIFAR shapes at B = 256; ImageNet-latent shapes at B = 64 (channel counts that are multiples of 192: N = 192 conv tiles,
+# the transposed CTA-pair weight-gradient kernel, a concatenated decoder input, the qkv 1x1 conv)
+@pytest.mark.parametrize("B,H,Cin,Cout,ks", [(256, 32, 256, 256, 3), (256, 16, 512, 256, 3), (256, 16, 256, 768, 1),
+                                             (256, 8, 256, 256, 3), (64, 64, 192, 192, 3), (64, 32, 576, 384, 3),
+                                             (64, 16, 576, 1728, 1)])
+def test_conv_triple_bilinear_identities_at_batch_256(dev, B, H, Cin, Cout, ks):
     from tinyedm_b200 import ops
     from tinyedm_b200.engine import WeightBank, conv_slot
     ops.ensure_device(dev)
     torch.manual_seed(H + Cin)
-    B = 256
     p = torch.nn.Parameter(torch.randn(Cout, Cin, ks, ks, device=dev))
     bank = WeightBank([conv_slot("w", p)])
     bank.materialise(dev)
