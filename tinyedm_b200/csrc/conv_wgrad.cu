@@ -9,8 +9,14 @@
 // The zero padding of the shifted X tile comes from TMA out-of-bounds fill, the G tile uses the same
 // 4-D box so both operands hold exactly the same pixel set (rows beyond the image are zero in both).
 //
-// Work item = (co block of 128, tap, ci block of <=256, K split). Accumulator 128 x 256 fp32 in TMEM.
-// Split-K partial results are combined with fp32 vector atomics into a zeroed dW.
+// Three kernels, chosen by conv_wgrad_launch:
+//   conv_wgrad_pair_kernel    CTA pair, M = 256 output channels, N <= 256 input channels of one tap (Cout % 256 == 0,
+//                             Cin % 128 == 0): the CIFAR net
+//   conv_wgrad_pair_t_kernel  CTA pair, dW held transposed: M = 4 slabs of the flattened (tap, ci) axis, N = output
+//                             channels in blocks of 256 / 192 / 128: every other multiple of 64 (ImageNet-latent, MNIST)
+//   conv_wgrad_kernel         single CTA, work item = (co block of 128, tap, ci block of <= 256, K split), accumulator
+//                             128 x 256 fp32 in TMEM, split-K partial results combined with fp32 vector atomics: the rest
+//                             (Cout < 128, fewer than 3 k slabs) and the A/B baseline (TEDM_CONV_PAIR=0, splits = -1)
 #include <cstdlib>
 
 #include "common.cuh"
