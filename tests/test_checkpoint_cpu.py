@@ -61,3 +61,37 @@ def test_swap_tensors():
     a, b = torch.arange(4.0), torch.ones(4)
     T.swap_tensors(a, b)
     assert torch.equal(a, torch.ones(4)) and torch.equal(b, torch.arange(4.0))
+
+
+def test_optimizer_state_dict_layouts_round_trip_on_cpu():
+    """`FusedAdamEMA.state_dict()` is the reference's EMAOptimizer layout (ema.py:326-336) around torch's Adam
+    layout; `load_state_dict` takes it back (and a plain Adam state dict too) without touching a device — the flat
+    kernel buffers are built from the loaded tensors at the first step on the GPU."""
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(4, 3)), torch.nn.Parameter(torch.randn(()))]
+    ref = torch.optim.Adam(ps, lr=0.02, betas=(0.9, 0.999))
+    for p in ps:
+        p.grad = torch.randn_like(p)
+    ref.step(); ref.step()
+    ema = tuple(p.detach() * 0.5 for p in ps)
+    ref_sd = {"opt": ref.state_dict(), "ema": ema, "current_step": 2, "gamma": 6.94, "every_n_steps": 1}
+    opt = T.FusedAdamEMA(ps, lr=1.0, ema_length=0.13)
+    opt.load_state_dict(ref_sd)
+    assert opt.current_step == 2 and abs(opt.gamma - 6.94) < 1e-12 and opt.param_groups[0]["lr"] == 0.02
+    sd = opt.state_dict()
+    assert set(sd) == {"opt", "ema", "current_step", "gamma", "every_n_steps"}
+    for i, p in enumerate(ps):
+        assert torch.equal(sd["opt"]["state"][i]["exp_avg"], ref.state[p]["exp_avg"])
+        assert torch.equal(sd["opt"]["state"][i]["exp_avg_sq"], ref.state[p]["exp_avg_sq"])
+        assert float(sd["opt"]["state"][i]["step"]) == 2.0
+        assert torch.equal(sd["ema"][i], ema[i])
+    torch.optim.Adam(ps, lr=0.1).load_state_dict(sd["opt"])        # the reference's optimiser accepts the Adam part
+    # plain Adam layout into an optimiser without EMA: step count recovered from the per-parameter `step`
+    plain = T.FusedAdamEMA(ps, lr=1.0)
+    plain.load_state_dict(ref.state_dict())
+    assert plain.current_step == 2 and set(plain.state_dict()) == {"state", "param_groups"}
+    try:
+        opt.load_state_dict({**ref_sd, "ema": ema[:1]})
+        assert False, "a wrong number of EMA tensors must raise"
+    except RuntimeError as e:
+        assert "EMA tensors" in str(e)

@@ -30,8 +30,36 @@ def reference(qkv: torch.Tensor, heads: int):
     return y.permute(0, 2, 1, 3).reshape(B, S, C)
 
 
+def reference_bf16(qkv: torch.Tensor, heads: int, g_y: torch.Tensor):
+    """The reference's OWN arithmetic under bf16 autocast on this GPU (networks.py:194-202 with a bf16 qkv: norm in fp32,
+    cast to bf16 before the divide (:14), fused bf16 SDPA and torch autograd): returns (y, d qkv). Its distance from the
+    fp32 evaluation of the same graph is the noise floor of the path this library replaces."""
+    B, S, C3 = qkv.shape
+    C = C3 // 3
+    hd = C // heads
+    x = qkv.detach().clone().requires_grad_(True)
+    t = x.view(B, S, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    n = torch.linalg.vector_norm(t, dim=-1, keepdim=True, dtype=torch.float32) / math.sqrt(hd)
+    t = t / (1e-4 + n).to(t.dtype)
+    y = F.scaled_dot_product_attention(t[0], t[1], t[2]).permute(0, 2, 1, 3).reshape(B, S, C)
+    (g,) = torch.autograd.grad(y, x, g_y.to(y.dtype))
+    return y.detach(), g
+
+
+NORTH_STAR_TOL = 1e-2     # bf16 per-layer relative L2
+
+
+def _assert_within(r: float, floor: float, what):
+    """<= 1e-2 (north_star), or — where bf16 itself cannot do that — no worse than the reference's own bf16 path on the
+    same inputs (both numbers are printed)."""
+    assert r < NORTH_STAR_TOL or r <= floor, (what, f"ours {r:.3e}", f"reference bf16 path {floor:.3e}")
+
+
 @pytest.mark.parametrize("B,H,W,heads,hd", [(3, 16, 16, 4, 64), (5, 8, 8, 4, 64), (3, 8, 8, 3, 64), (1, 8, 8, 1, 64),
-                                            (2, 14, 14, 4, 64), (2, 7, 7, 4, 128), (2, 16, 16, 4, 144)])
+                                            (2, 14, 14, 4, 64), (2, 7, 7, 4, 128), (2, 16, 16, 4, 144), (2, 8, 8, 4, 192),
+                                            # the configs' own batch sizes: CIFAR train 256 / sampling 128, MNIST 128
+                                            (256, 16, 16, 4, 64), (256, 8, 8, 4, 64), (128, 14, 14, 4, 64), (128, 7, 7, 4, 128),
+                                            (64, 16, 16, 4, 144), (64, 8, 8, 4, 192)])
 def test_attention_forward_backward_vs_torch(dev, B, H, W, heads, hd):
     from tinyedm_b200 import ops
     ops.ensure_device(dev)
@@ -54,7 +82,11 @@ def test_attention_forward_backward_vs_torch(dev, B, H, W, heads, hd):
     g_qkv = ops.attention_backward(qkv, y, g_y, lse, heads)
     (g_ref,) = torch.autograd.grad(ref, x, g_y.float().view(B, H * W, C))
     rg = rel(g_qkv.view(B, H * W, 3 * C), g_ref)
-    assert rg < 3e-2, rg
+    y16, g16 = reference_bf16(qkv.view(B, H * W, 3 * C), heads, g_y.view(B, H * W, C))
+    floor_f, floor_b = rel(y16, ref), rel(g16, g_ref)
+    print(f"attention B={B} S={H * W} hd={hd}: forward {r:.2e} (reference bf16 path {floor_f:.2e}), "
+          f"backward {rg:.2e} (reference bf16 path {floor_b:.2e})")
+    _assert_within(rg, floor_b, "d qkv")
 
 
 @pytest.mark.parametrize("B,heads", [(2, 4), (3, 1), (41, 4), (5, 3)])
@@ -76,9 +108,13 @@ def test_attention_backward_s256_each_gradient(dev, B, heads):
     (g_ref,) = torch.autograd.grad(ref, x, g_y.float().view(B, H * W, C))
     g_ref = g_ref.view(B, H * W, 3, C)
     assert torch.isfinite(g_qkv).all()
+    _, g16 = reference_bf16(qkv.view(B, H * W, 3 * C), heads, g_y.view(B, H * W, C))
+    g16 = g16.view(B, H * W, 3, C)
     for part, name in enumerate("qkv"):
         r = rel(g_qkv[:, :, part], g_ref[:, :, part])
-        assert r < 1.5e-2, (name, r)
+        floor = rel(g16[:, :, part], g_ref[:, :, part])
+        print(f"attention backward S=256 B={B} heads={heads}: d{name} {r:.2e} (reference bf16 path {floor:.2e})")
+        _assert_within(r, floor, "d" + name)
     # deterministic: no atomics anywhere in the backward
     again = ops.attention_backward(qkv, y, g_y, lse, heads).view(B, H * W, 3, C).float()
     assert torch.equal(again, g_qkv)

@@ -42,7 +42,13 @@ def _silu_grad(x):
 CASES = [(40, 32, 32, 256, 256, 3), (41, 16, 16, 256, 256, 3), (150, 8, 8, 256, 256, 3), (40, 16, 16, 256, 768, 1),
          (24, 28, 28, 128, 128, 3), (90, 14, 14, 256, 256, 1), (12, 64, 64, 192, 192, 3), (161, 7, 7, 512, 512, 1),
          # tail split: 100 resp. 150 pair tiles on 74 CTA pairs leave 26 resp. 2 tiles, cut into half-N work items
-         (100, 16, 16, 256, 256, 3), (50, 16, 16, 256, 768, 1)]
+         (100, 16, 16, 256, 256, 3), (50, 16, 16, 256, 768, 1),
+         # BASELINE.json's own batch sizes, element-wise: training B = 256 at every CIFAR level (the
+         # headline launch: 1 024 pair tiles in 14 waves), the concatenated decoder input, the qkv conv; sampling B = 128
+         (256, 32, 32, 256, 256, 3), (256, 16, 16, 256, 256, 3), (256, 8, 8, 256, 256, 3), (256, 16, 16, 512, 256, 3),
+         (256, 16, 16, 256, 768, 1), (128, 32, 32, 256, 256, 3), (128, 16, 16, 256, 256, 3), (128, 8, 8, 256, 256, 3),
+         # ImageNet-latent micro-batch 176 (imagenet.yaml:14) at its first level, MNIST batch 128
+         (176, 64, 64, 192, 192, 3), (128, 28, 28, 128, 128, 3)]
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,ks", CASES)
@@ -107,7 +113,10 @@ def test_pair_conv_epilogues_vs_torch(dev, B, H, W, Cin, Cout, ks):
                                                (3, 64, 64, 192, 192, 3), (5, 32, 32, 384, 384, 3), (4, 16, 16, 576, 576, 3),
                                                (4, 32, 32, 576, 384, 3), (6, 16, 16, 576, 1728, 1), (2, 28, 28, 128, 128, 3),
                                                (3, 16, 16, 1344, 768, 3), (2, 8, 8, 768, 576, 1), (9, 8, 8, 64, 128, 3),
-                                               (3, 16, 16, 128, 320, 3), (12, 64, 64, 192, 192, 3), (5, 7, 7, 128, 384, 3)])
+                                               (3, 16, 16, 128, 320, 3), (12, 64, 64, 192, 192, 3), (5, 7, 7, 128, 384, 3),
+                                               # BASELINE.json's training batch, element-wise
+                                               (256, 32, 32, 256, 256, 3), (256, 16, 16, 512, 256, 3), (256, 8, 8, 256, 256, 3),
+                                               (256, 16, 16, 256, 768, 1), (176, 64, 64, 192, 192, 3)])
 def test_pair_wgrad_vs_torch_and_single(dev, B, H, W, Cin, Cout, ks):
     from tinyedm_b200 import ops
     ops.ensure_device(dev)
@@ -124,3 +133,36 @@ def test_pair_wgrad_vs_torch_and_single(dev, B, H, W, Cin, Cout, ks):
         dws = torch.full((Cout, ks * ks, Cin), 3.0, device=dev)
         ops.conv2d_wgrad(g, x, dws, ks, alpha=0.5, accumulate=acc, splits=-1)      # single-CTA kernel (vector atomics)
         assert rel(dw, dws) < 1e-4
+
+
+@pytest.mark.parametrize("B,H,W,Cin,C1,C2", [(40, 32, 32, 256, 256, 256), (150, 8, 8, 256, 256, 256), (256, 32, 32, 256, 256, 256),
+                                             (256, 16, 16, 256, 256, 256)])
+def test_dgrad_split_epilogue_vs_torch(dev, B, H, W, Cin, C1, C2):
+    """tedm_conv2d_dgrad_split element-wise against fp32 torch: g_cat = alpha * dgrad * mp_silu'(x) + beta * res split into
+    g_in (+ accumulation + per-(image, channel) bias), g_skip * gain and the reduction sum_pixels g_cat * x (autograd of
+    networks.py:309-316 through :106-118's gain)."""
+    from tinyedm_b200 import ops
+    ops.ensure_device(dev)
+    if not ops.conv2d_dgrad_split_supported(B, H, W, Cin, C1, C2, 3):
+        pytest.skip("launch too small for the CTA-pair kernel")
+    torch.manual_seed(B + H)
+    Ct = C1 + C2
+    g = torch.randn(B, H, W, Cin, device=dev).to(BF)
+    w = torch.randn(Ct, Cin, 3, 3, device=dev) / math.sqrt(Cin * 9)
+    acc = _ref_conv(g, w)
+    x = torch.randn(B, H, W, Ct, device=dev).to(BF)
+    res = torch.randn(B, H, W, Ct, device=dev).to(BF)
+    gain = torch.rand(B, C2, device=dev) * 0.8 + 0.1
+    bias = torch.randn(B, C1, device=dev)
+    old = torch.randn(B, H, W, C1, device=dev).to(BF)
+    g_cat = 0.9 * acc * _silu_grad(x.float()) + 0.7 * res.float()
+    for accumulate in (False, True):
+        g_in = old.clone()
+        g_skip = torch.empty(B, H, W, C2, device=dev, dtype=BF)
+        d_gx = torch.zeros(B, C2, device=dev)
+        ops.conv2d_dgrad_split(g, _wq(w), 3, x=x, res=res, beta=0.7, gain=gain, g_in=g_in, g_skip=g_skip, d_gx=d_gx,
+                               accumulate_in=accumulate, alpha=0.9, in_bias=bias if accumulate else None, in_bias_scale=0.25)
+        want_in = g_cat[..., :C1] + ((old.float() + 0.25 * bias[:, None, None, :]) if accumulate else 0.0)
+        assert rel(g_in, want_in) < 6e-3
+        assert rel(g_skip, g_cat[..., C1:] * gain[:, None, None, :]) < 6e-3
+        assert rel(d_gx, (g_cat[..., C1:] * x[..., C1:].float()).sum(dim=(1, 2))) < 5e-3

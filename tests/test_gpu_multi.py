@@ -75,6 +75,22 @@ def _worker(rank, world, port, out):
             assert err < tol, (n, err)
             worst = max(worst, err)
         assert len(ddp._plan) >= 3
+        # gradient accumulation under no_sync (imagenet.yaml:7 `accumulate_grad_batches`): two micro-batches per rank, ONE
+        # exchange and one weight-norm Jacobian on the second; same gradients as the whole batch in one process
+        model.zero_grad(set_to_none=True)
+        mid = (sl.start + sl.stop) // 2
+        for j, (a, b) in enumerate(((sl.start, mid), (mid, sl.stop))):
+            with ddp.no_sync(j == 0):
+                (_loss(model, clean[a:b], sigma[a:b], noise[a:b], labels[a:b]) / 2).backward()
+            if j == 0:
+                assert model.denoiser.conv_in.weight.grad is None
+        ddp.finish_backward()
+        torch.cuda.synchronize()
+        for n, p in model.named_parameters():
+            a, b = p.grad.double(), ref_grads[n].double()
+            err = float((a - b).norm() / (b.norm() + 1e-12))
+            assert err < (0.15 if p.ndim == 0 else 4e-2), ("accumulated", n, err)
+            worst = max(worst, err)
         # batch-sharded sampling == unsharded sampling (no collective on the path)
         solver = T.DeterministicSolver(num_steps=4)
         full = solver.solve(model, x0, labels)

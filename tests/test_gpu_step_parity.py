@@ -1,0 +1,261 @@
+"""The step-level surfaces around the denoiser, CUDA path vs the oracle / the reference's golden vectors:
+`Diffuser.forward` (edm.py:84-93), `EDM.validation_step` (:238-248), `EDM.predict_step` (:288-295), gradient accumulation
+(imagenet.yaml:7 `accumulate_grad_batches: 3`), the optimiser's checkpoint round trip (ema.py:326-348) and the EMA weight
+swap (ema.py:293-317) with the eval-mode cache of normalised weights."""
+import copy
+
+import pytest
+import torch
+
+from oracle import edm2_oracle as O
+from tests.helpers import SMALL, build_modules, rel, small_params
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from tinyedm_b200 import ops
+    d = torch.device("cuda:0")
+    ops.ensure_device(d)
+    return d
+
+
+def _small_edm(dev, use_uncertainty=False, **kw):
+    import tinyedm_b200 as T
+    dp, ep, up = small_params()
+    den, emb_m, unc = build_modules(SMALL, dp, ep, up, dev)
+    args = dict(use_ema=False, use_uncertainty=use_uncertainty, steady_steps=1, rampup_steps=1, scheduler_interval="step")
+    args.update(kw)
+    model = T.EDM(diffuser=T.Diffuser(-1.2, 1.2), embedding=emb_m, denoiser=den, **args)
+    if use_uncertainty:
+        model.u = unc
+    return model.to(dev), (dp, ep, up)
+
+
+def test_diffuse_kernel_vs_reference_golden(dev, golden):
+    """tedm_diffuse against the reference's own numbers (oracle/make_golden.py stores edm.py:84-93 evaluated by torch on
+    the committed eps / noise draws): fp32, <= 1e-6."""
+    from tinyedm_b200 import ops
+    clean, eps, noise = (torch.from_numpy(golden[k]).to(dev) for k in ("clean", "eps", "noise"))
+    noisy, sigma = ops.diffuse(clean, eps, noise, -1.2, 1.2)
+    assert noisy.shape == clean.shape and sigma.shape == (clean.shape[0],)
+    assert rel(sigma, golden["sigma"]) < 1e-6
+    assert rel(noisy, golden["noisy"]) < 1e-6
+    no, so = O.diffuse(clean.cpu(), eps.cpu(), noise.cpu(), -1.2, 1.2)
+    assert rel(noisy, no) < 1e-6 and rel(sigma, so) < 1e-6
+    # other (P_mean, P_std) and a batch that is not a multiple of anything
+    g = torch.Generator().manual_seed(0)
+    c2, e2, n2 = torch.randn(7, 4, 64, 64, generator=g), torch.randn(7, generator=g), torch.randn(7, 4, 64, 64, generator=g)
+    noisy2, sigma2 = ops.diffuse(c2.to(dev), e2.to(dev), n2.to(dev), -0.4, 1.0)
+    no2, so2 = O.diffuse(c2, e2, n2, -0.4, 1.0)
+    assert rel(noisy2, no2) < 1e-6 and rel(sigma2, so2) < 1e-6
+
+
+def test_diffuser_module_statistics_and_freshness(dev):
+    """`Diffuser.forward`: ln(sigma) ~ N(P_mean, P_std), noise ~ N(0, sigma^2) independent of the image, new draws on
+    every call, no gradient (edm.py:84 `@torch.no_grad`)."""
+    import tinyedm_b200 as T
+    torch.manual_seed(123)
+    diff = T.Diffuser(-1.2, 1.2)
+    clean = torch.zeros(4096, 3, 8, 8, device=dev)
+    noisy, sigma = diff(clean)
+    assert not noisy.requires_grad and sigma.shape == (4096,)
+    ls = sigma.log()
+    assert abs(float(ls.mean()) + 1.2) < 0.08 and abs(float(ls.std()) - 1.2) < 0.08
+    z = noisy / sigma.view(-1, 1, 1, 1)                       # unit normal draws
+    assert abs(float(z.mean())) < 5e-3 and abs(float(z.std()) - 1.0) < 5e-3
+    assert abs(float((z[:, 0] * z[:, 1]).mean())) < 1e-2      # channels uncorrelated
+    noisy2, sigma2 = diff(clean)
+    assert not torch.equal(sigma, sigma2) and not torch.equal(noisy, noisy2)
+
+
+def test_validation_step_vs_oracle(dev):
+    """edm.py:238-248 on the CUDA path: the (noisy, sigma) the diffuser produced are taken from a forward hook and pushed
+    through the fp32 oracle (embedding -> denoiser -> lambda(sigma)-weighted MSE); the bf16 network's accumulated drift
+    bounds the loss error. The running metric state follows metric.py:33-36."""
+    model, (dp, ep, _) = _small_edm(dev)
+    model.eval()
+    seen = {}
+    h = model.diffuser.register_forward_hook(lambda m, i, o: seen.update(noisy=o[0].detach().cpu(), sigma=o[1].detach().cpu()))
+    g = torch.Generator().manual_seed(3)
+    clean = (0.5 * torch.randn(6, 3, 16, 16, generator=g)).clamp(-1, 1)
+    labels = torch.randint(0, 5, (6,), generator=g)
+    torch.manual_seed(11)
+    with torch.no_grad():
+        loss = model.validation_step((clean.to(dev), labels.to(dev)), 0)
+    h.remove()
+    assert loss.shape == (1,)
+    # the diffuser's output is edm.py:84-93 of SOME draws: sigma positive, noisy - clean = sigma * unit normal
+    z = (seen["noisy"] - clean) / seen["sigma"].view(-1, 1, 1, 1)
+    assert abs(float(z.std()) - 1.0) < 0.05
+    _, emb = O.embedding_forward(ep, SMALL["embedding"], seen["sigma"], labels)
+    D_o = O.denoiser_forward(dp, SMALL["denoiser"], seen["noisy"], seen["sigma"], emb)
+    loss_o = O.training_loss(O.loss_weight(seen["sigma"], 0.5), D_o, clean)
+    r = rel(loss, loss_o)
+    print(f"validation_step loss vs fp32 oracle: {r:.2e}")
+    assert r < 4e-2
+    assert int(model.val_mse.total) == 6 and rel(model.val_mse.compute(), loss_o) < 4e-2
+    # an unconditional model ignores the labels it is handed (edm.py:240)
+    import tinyedm_b200 as T
+    dp2, ep2, _ = small_params()
+    ep2 = {k: v for k, v in ep2.items() if not k.startswith("class_embed")}
+    import dataclasses
+    cfg_u = dict(SMALL)
+    cfg_u["embedding"] = dataclasses.replace(SMALL["embedding"], num_classes=None)
+    den2, emb2, _ = build_modules(cfg_u, dp2, ep2, None, dev)
+    m2 = T.EDM(diffuser=T.Diffuser(-1.2, 1.2), embedding=emb2, denoiser=den2, use_ema=False, use_uncertainty=False,
+               steady_steps=1, rampup_steps=1, scheduler_interval="step").eval()
+    with torch.no_grad():
+        assert torch.isfinite(m2.validation_step((clean.to(dev), labels.to(dev)), 0)).all()
+
+
+def test_predict_step_vs_reference_golden(dev, golden):
+    """edm.py:288-295: `predict_step(batch)` == `solver.solve(self, x0, labels)`; against the reference's 6-step sample."""
+    import tinyedm_b200 as T
+    model, _ = _small_edm(dev)
+    model.eval()
+    model.solver = T.DeterministicSolver(num_steps=int(golden["sampler_steps"]))
+    x0 = torch.from_numpy(golden["x0"]).to(dev)
+    labels = torch.from_numpy(golden["labels"]).to(dev)
+    out = model.predict_step((x0, labels), 0)
+    assert out.shape == x0.shape and out.dtype == torch.float32
+    r = rel(out, golden["sampler_out"])
+    print(f"predict_step (6-step Heun, bf16 network) vs fp32 reference: {r:.2e}")
+    assert r < 4e-2
+    assert torch.equal(out, model.solver.solve(model, x0, labels))
+
+
+def _grads_of(model):
+    return {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+
+
+def test_gradient_accumulation_equals_one_big_batch(dev):
+    """3 micro-batches with deferred hand-out (one Jacobian, one exchange) == the gradient of the mean loss over the three,
+    computed micro-batch by micro-batch through plain autograd accumulation, and == Lightning's semantics (loss / k)."""
+    import tinyedm_b200 as T
+    model, _ = _small_edm(dev, use_uncertainty=True)
+    model.eval()                                # eval: no dropout, weights stay put -> the two routes see identical inputs
+    g = torch.Generator().manual_seed(8)
+    k, mb = 3, 4
+    clean = (0.5 * torch.randn(k * mb, 3, 16, 16, generator=g)).clamp(-1, 1).to(dev)
+    labels = torch.randint(0, 5, (k * mb,), generator=g).to(dev)
+    state = torch.cuda.get_rng_state(dev)
+
+    def run(deferred: bool):
+        model.zero_grad(set_to_none=True)
+        torch.cuda.set_rng_state(state, dev)
+        for j in range(k):
+            batch = (clean[j * mb:(j + 1) * mb], labels[j * mb:(j + 1) * mb])
+            with model.denoiser.accumulate_grads(deferred and j < k - 1):
+                loss = model.training_step(batch, j) / k
+                loss.backward()
+            if deferred and j < k - 1:
+                assert model.denoiser.conv_in.weight.grad is None      # nothing handed out yet
+        return _grads_of(model)
+
+    g_plain = run(False)      # autograd accumulates three handed-out gradients
+    g_defer = run(True)       # g_hat accumulates, one hand-out
+    assert set(g_plain) == set(g_defer)
+    worst = max((rel(g_defer[n], g_plain[n]), n) for n in g_plain)
+    print("accumulation: deferred vs per-micro-batch hand-out, worst", worst)
+    assert worst[0] < 2e-5
+    # and a second optimiser step starts from a clean slate (the accumulator is reset by the hand-out)
+    g_again = run(True)
+    assert max(rel(g_again[n], g_defer[n]) for n in g_defer) < 2e-5
+
+
+def test_optimizer_state_round_trip_resumes_exactly(dev):
+    """save -> load -> step must continue the Adam moments, the EMA copies and the bias-correction step,
+    in the reference's EMAOptimizer layout (ema.py:326-348)."""
+    import tinyedm_b200 as T
+    torch.manual_seed(0)
+    shapes = [(64, 64, 3, 3), (130,), (), (16, 65, 1, 1)]
+    ps = [torch.nn.Parameter(torch.randn(s, device=dev)) for s in shapes]
+    opt = T.FusedAdamEMA(ps, lr=0.02, betas=(0.9, 0.999), ema_length=0.13)
+    grads = [[torch.randn_like(p) for p in ps] for _ in range(5)]
+    for step in range(3):
+        for p, gr in zip(ps, grads[step]):
+            p.grad = gr.clone()
+        opt.step()
+    sd = copy.deepcopy(opt.state_dict())
+    assert set(sd) == {"opt", "ema", "current_step", "gamma", "every_n_steps"} and sd["current_step"] == 3
+    assert len(sd["ema"]) == len(ps) and set(sd["opt"]["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+    # the Adam part loads into the reference's own optimiser (edm.py:250-253)
+    ref_ps = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    ref = torch.optim.Adam(ref_ps, lr=0.02, betas=(0.9, 0.999))
+    ref.load_state_dict(sd["opt"])
+    assert float(ref.state[ref_ps[0]]["step"]) == 3.0
+    # resume in a fresh optimiser over fresh parameter objects
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    opt2 = T.FusedAdamEMA(qs, lr=0.5, betas=(0.8, 0.9), ema_length=0.13)
+    opt2.load_state_dict(sd)
+    assert opt2.current_step == 3 and opt2.param_groups[0]["lr"] == 0.02 and tuple(opt2.param_groups[0]["betas"]) == (0.9, 0.999)
+    for e1, e2 in zip(opt.ema_params, opt2.ema_params):
+        assert torch.equal(e1, e2)
+    for step in range(3, 5):
+        for p, q, gr in zip(ps, qs, grads[step]):
+            p.grad = gr.clone(); q.grad = gr.clone()
+        opt.step(); opt2.step()
+    for p, q in zip(ps, qs):
+        assert torch.equal(p, q)
+    for e1, e2 in zip(opt.ema_params, opt2.ema_params):
+        assert torch.equal(e1, e2)
+    assert torch.equal(opt.state[ps[0]]["exp_avg_sq"], opt2.state[qs[0]]["exp_avg_sq"])
+    # every_n_steps > 1: the EMA moves only on steps whose 0-based index is a multiple of it (ema.py:262-269)
+    rs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    opt3 = T.FusedAdamEMA(rs, lr=0.02, ema_length=0.13, every_n_steps=2)
+    snaps = []
+    for step in range(4):
+        for r_, gr in zip(rs, grads[step]):
+            r_.grad = gr.clone()
+        opt3.step()
+        snaps.append(opt3.ema_params[0].clone())
+    assert torch.equal(snaps[0], snaps[1]) and not torch.equal(snaps[1], snaps[2]) and torch.equal(snaps[2], snaps[3])
+
+
+def test_ema_swap_invalidates_cached_normalised_weights(dev):
+    """`swap_tensors(param.data, ema)` bumps no version counter; the eval-mode weight cache must still
+    notice (ema.py:293-296 is how the reference validates and samples with EMA weights)."""
+    import tinyedm_b200 as T
+    model, _ = _small_edm(dev)
+    model.eval()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(3, 3, 16, 16, generator=g).to(dev)
+    sigma = torch.tensor([0.5, 1.0, 2.0], device=dev)
+    labels = torch.tensor([0, 1, 2], device=dev)
+    with torch.no_grad():
+        d_a = model(x, sigma, labels).clone()
+        other = [torch.randn_like(p) if p.ndim > 1 else p.detach().clone() for p in model.parameters()]
+        for p, o in zip(model.parameters(), other):
+            T.swap_tensors(p.data, o)
+        d_b = model(x, sigma, labels).clone()
+        assert rel(d_b, d_a) > 1e-2, "the swapped-in weights were ignored (stale cache)"
+        for p, o in zip(model.parameters(), other):
+            T.swap_tensors(p.data, o)
+        assert torch.equal(model(x, sigma, labels), d_a)
+        # raw `.data` writes + the explicit hook
+        for p in model.parameters():
+            if p.ndim > 1:
+                p.data.mul_(-1.0)
+        model.invalidate_weights()
+        d_c = model(x, sigma, labels)
+        assert rel(d_c, d_a) > 1e-2
+    # the optimiser's own swap (ema.py:299-317)
+    model.train()
+    opt = T.FusedAdamEMA(model.parameters(), lr=1e-2, ema_length=0.13)
+    clean = torch.randn(4, 3, 16, 16, generator=g).clamp(-1, 1).to(dev)
+    for i in range(2):
+        opt.zero_grad(set_to_none=True)
+        model.training_step((clean, torch.zeros(4, dtype=torch.long, device=dev)), i).backward()
+        opt.step()
+    model.eval()
+    with torch.no_grad():
+        d_w = model(x, sigma, labels).clone()
+        with opt.swap_ema_weights():
+            d_e = model(x, sigma, labels).clone()
+        assert not torch.equal(d_e, d_w)
+        assert torch.equal(model(x, sigma, labels), d_w)

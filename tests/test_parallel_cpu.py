@@ -24,6 +24,15 @@ def test_plan_buckets_tiles_the_buffer_from_the_end():
         plan_buckets([(900, 1000), (500, 800)], 10)                                  # gap
 
 
+def test_plan_buckets_lone_tail_keeps_the_last_message_small():
+    units = [(900, 1000), (600, 900), (590, 600), (200, 590), (0, 200)]
+    b = plan_buckets(units, 300, lone_tail=True)
+    assert [(x.start, x.end, x.ready_after) for x in b] == [(600, 1000, 1), (200, 600, 3), (0, 200, 4)]
+    b = plan_buckets(units, 10 ** 9, lone_tail=True)      # even with one huge bucket the last unit travels alone
+    assert [(x.start, x.end, x.ready_after) for x in b] == [(200, 1000, 3), (0, 200, 4)]
+    assert [(x.start, x.end) for x in plan_buckets(units[:1], 10, lone_tail=True)] == [(900, 1000)]
+
+
 def test_cifar_engine_units_tile_the_ghat_buffer():
     import tinyedm_b200 as T
     from oracle import edm2_oracle as O

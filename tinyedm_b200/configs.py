@@ -25,7 +25,7 @@ MNIST = dict(
         skip_connections=(False, False, True, True, True, True, False, True, True, True, True, False, True, True, True, True)),
     embedding=dict(fourier_dim=64, embedding_dim=256, num_classes=10),
     diffuser=dict(P_mean=-1.2, P_std=1.2),
-    edm=dict(use_ema=False, ema_length=None, use_uncertainty=False, lr=0.01, steady_steps=200, rampup_steps=200,
+    edm=dict(use_ema=False, ema_length=0.1, use_uncertainty=False, lr=0.01, steady_steps=500, rampup_steps=500,
              scheduler_interval="epoch"),
     image=(1, 28, 28), batch=128)
 

@@ -882,7 +882,8 @@ int sgemm(const float* A, const float* B, float* C, int M, int N, int K, int lda
   // long-K, few-tile problems (e.g. g_emb = d_lin (B x 5376) W (5376 x 256)) would run on a handful of CTAs: split K
   int splits = 1;
   const int tiles = grid.x * grid.y;
-  if (beta == 0.f && ((K >= 1024 && tiles < num_sms()) || (K >= 128 && tiles <= 8))) {
+  // (beta == 1: the partial sums are atomically added onto the existing C, no memset)
+  if ((beta == 0.f || beta == 1.f) && ((K >= 1024 && tiles < num_sms()) || (K >= 128 && tiles <= 8))) {
     splits = 2 * num_sms() / tiles;
     const int max_splits = K >= 1024 ? K / 256 : K / 32;   // tiny problems are latency bound: 2 k-steps per CTA
     if (splits > max_splits) splits = max_splits;
@@ -894,7 +895,7 @@ int sgemm(const float* A, const float* B, float* C, int M, int N, int K, int lda
   grid.z = splits;
   if (splits > 1) {
     TEDM_CHECK(ldc == N, "sgemm: split-K needs a dense C");
-    TEDM_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, stream));
+    if (beta == 0.f) TEDM_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, stream));
   }
   launch_pdl(sgemm_kernel, grid, 256, 0, stream, A, B, C, M, N, K, lda, ldb, ldc, transA, transB, alpha, beta, k_chunk);
   TEDM_LAUNCH_CHECK();

@@ -84,6 +84,8 @@ class EDM(_Base):
         self.train_mse = WeightedMeanSquaredError()
         self.val_mse = WeightedMeanSquaredError()
         self.solver = None
+        if HAVE_LIGHTNING:  # pragma: no cover - the reference's checkpoints carry the deinstantiate tree (edm.py:154-157)
+            self.hparams.update(self.save_config())
 
     # ---- Lightning shims (no-ops without Lightning) ----
     if not HAVE_LIGHTNING:
@@ -92,6 +94,11 @@ class EDM(_Base):
 
         def lr_schedulers(self):
             return None
+
+    def _log_metric(self, name: str, metric, **kw) -> None:
+        """The reference logs the torchmetrics object itself; this metric is a plain module, so log its running value."""
+        if HAVE_LIGHTNING:  # pragma: no cover
+            self.log(name, metric.compute().reshape(()), **kw)
 
     def _log_lr(self) -> None:
         sched = self.lr_schedulers()
@@ -108,7 +115,7 @@ class EDM(_Base):
         denoised_image = self.denoiser(noisy_image, sigma, embedding)
         uncertainty = self.u(fourier_embedding).flatten() if self.u is not None else None
         loss = self.train_mse.edm_loss(denoised_image, clean_image, sigma, self.sigma_data, uncertainty)
-        self.log("train_loss", self.train_mse, prog_bar=True)
+        self._log_metric("train_loss", self.train_mse, prog_bar=True)
         if uncertainty is not None:
             self.log("uncertainty", uncertainty.detach().mean())
         self._log_lr()
@@ -122,7 +129,7 @@ class EDM(_Base):
         _, embedding = self.embedding(sigma, class_label)
         denoised_image = self.denoiser(noisy_image, sigma, embedding)
         loss = self.val_mse.edm_loss(denoised_image, clean_image, sigma, self.sigma_data)
-        self.log("val_loss", self.val_mse)
+        self._log_metric("val_loss", self.val_mse)
         return loss
 
     def forward(self, noisy_image: Tensor, sigma: Tensor, class_label: Tensor | None = None) -> Tensor:
@@ -142,6 +149,12 @@ class EDM(_Base):
         """edm.py:154-157: the `deinstantiate` tree of this module (what the reference stores as `hyper_parameters`)."""
         from .utils import deinstantiate
         return deinstantiate(self)
+
+    def invalidate_weights(self) -> None:
+        """Call after writing parameters through `.data` (which bumps no version counter): the cached normalised weights
+        of the embedding, the denoiser and the uncertainty head are rebuilt at the next forward."""
+        from .engine import bump_weights_epoch
+        bump_weights_epoch()
 
     def prepare_weights(self, device) -> None:
         """Refreshes the cached normalised weights of the embedding and the denoiser (no-op while they are current);
@@ -167,7 +180,7 @@ class EDM(_Base):
     def configure_optimizers(self):
         from .optim import FusedAdamEMA
         optimizer = FusedAdamEMA(self.parameters(), lr=self.lr, betas=self.betas,
-                                 ema_length=self.ema_length if self.use_ema else None)
+                                 ema_length=self.ema_length if self.use_ema else None, every_n_steps=self.every_n_steps)
         scheduler = self.get_lr_scheduler(optimizer, self.rampup_steps, self.steady_steps)
         return {"optimizer": optimizer,
                 "lr_scheduler": {"scheduler": scheduler, "interval": self.scheduler_interval, "frequency": 1}}

@@ -42,6 +42,17 @@ def _round_up(n: int, m: int) -> int:
     return (n + m - 1) // m * m
 
 
+# Writes through `param.data` (the reference's EMA swap: ema.py:293-296 via utils.swap_tensors; dist.broadcast of
+# `t.data`) do not bump `param._version`, so the eval-mode cache of prepared weights is also keyed on this process-wide
+# epoch: `swap_tensors`, `FusedAdamEMA.switch_main_parameter_weights`, `DistributedEDM` and `EDM.invalidate_weights` bump it.
+_WEIGHTS_EPOCH = [0]
+
+
+def bump_weights_epoch() -> None:
+    """Invalidates every cached set of normalised weights in this process (they are rebuilt at the next forward)."""
+    _WEIGHTS_EPOCH[0] += 1
+
+
 # =========================================================================================================
 # Weight bank
 # =========================================================================================================
@@ -82,6 +93,7 @@ class WeightBank:
         self._table: Tensor | None = None
         self._table_ptrs = None
         self._have_grad_buffers = False
+        self.aux_elems = 0      # fp32 scratch at the FRONT of the flat g_hat buffer (the engine keeps its 0-d gradients there)
         self.total_rows = sum(s.rows for s in slots)
         self.total_groups = sum((s.rows + 15) // 16 for s in slots)     # 16 prepared rows per CTA of weight_prep_fwd
         self.max_row_floats = max(s.taps * (s.cin + 4) for s in slots)  # staging of one dL/dw_hat row in weight_prep_bwd
@@ -122,11 +134,12 @@ class WeightBank:
     def ensure_grad_buffers(self) -> None:
         if self._have_grad_buffers:
             return
-        n_gh = sum(_round_up(s.rows * s.kpad, _ALIGN) for s in self.slots)
+        aux = _round_up(self.aux_elems, _ALIGN)
+        n_gh = aux + sum(_round_up(s.rows * s.kpad, _ALIGN) for s in self.slots)
         n_gr = sum(_round_up(s.param.numel(), _ALIGN) for s in self.slots)
         self._ghat_flat = torch.zeros(n_gh, device=self.device, dtype=F32)
         self.grad_flat = torch.zeros(n_gr, device=self.device, dtype=F32)
-        og = orr = 0
+        og, orr = aux, 0
         for s in self.slots:
             s.ghat = self._ghat_flat[og:og + s.rows * s.kpad].view(s.rows, s.kpad)
             s.grad = self.grad_flat[orr:orr + s.param.numel()].view_as(s.param)
@@ -204,7 +217,7 @@ class WeightBank:
             torch.autograd.graph.increment_version([s.param for s in self.slots])
             self._key = None
             return
-        key = tuple(s.param._version for s in self.slots)
+        key = (_WEIGHTS_EPOCH[0],) + tuple(s.param._version for s in self.slots)
         if key != self._key:
             ops.weight_prep_forward(self._table, len(self.slots), self.total_groups, False)
             self._key = key
@@ -271,7 +284,12 @@ class DenoiserEngine:
         self.blocks: list[BlockPlan] = []
         self._aux_key = None
         self.grad_sync = None   # set by parallel.DistributedEDM: overlaps the gradient all-reduce with this backward
-        self._sg: Tensor | None = None   # persistent gradients of the 0-d parameters (block gains..., gain_out)
+        # gradient accumulation (imagenet.yaml:7 `accumulate_grad_batches: 3`): while `defer_grads` is set a backward only
+        # ADDS its dL/dw_hat to the flat g_hat buffer (which also holds the 0-d gradients); the first backward with it
+        # cleared applies the weight-norm Jacobian to the sum, exchanges it between ranks and hands out the gradients
+        self.defer_grads = False
+        self._accum = 0         # micro-batches already summed into g_hat since the last hand-out
+        self._sg_alive = False  # 0-d `.grad`s of an earlier backward are still referenced (plain autograd accumulation)
         self._build_plan()
 
     # ---- static plan ----
@@ -343,6 +361,9 @@ class DenoiserEngine:
         if m.embedding_dim % 2 != 0:
             raise RuntimeError("tinyedm_b200: embedding_dim must be even")
         self.bank = WeightBank(embed_slots + slots)
+        # the gradients of the 0-d parameters (block gains..., gain_out) live at the front of the flat g_hat buffer: the
+        # one memset of a backward clears them and the trailing data-parallel message carries them (no collective of their own)
+        self.bank.aux_elems = len(self.blocks) + 1
         for c in (list(m.encoder_out_channels) + list(m.decoder_out_channels)):
             if c % 64 != 0:
                 raise RuntimeError(f"tinyedm_b200: channel counts must be multiples of 64 (got {c})")
@@ -400,8 +421,12 @@ class DenoiserEngine:
         if save:
             self.bank.ensure_grad_buffers()
         drop_p = float(m.dropout_rate) if training else 0.0
+        seed_t = self.step_counter
         if training and drop_p > 0:
             self.step_counter += 1
+            # per-forward snapshot: the backward regenerates THIS forward's masks even if another training forward ran
+            # in between (two micro-batches, then their backwards)
+            seed_t = self.step_counter.clone() if save else self.step_counter
 
         # ---- modulation for every block: m = embed(emb) * gain + 1 (networks.py:255-258, :319-322) ----
         N = self.n_mod
@@ -423,7 +448,7 @@ class DenoiserEngine:
         ctx = None
         if save:
             ctx = dict(B=B, H=H, W=W, noisy=noisy, sigma=sigma, emb=emb, lin=lin, mod=mod, xcol=xcol, blocks=[],
-                       drop_p=drop_p, Be=Be)
+                       drop_p=drop_p, Be=Be, seed=seed_t)
         skips = [x]
         means = [mean0]
         n_pushed = 1
@@ -433,7 +458,7 @@ class DenoiserEngine:
                 skip = skips.pop()
                 mean = means.pop()
             want_mean = bp.kind == "enc" and used[n_pushed]
-            x, saved, out_mean = self._block_forward(bp, x, skip, mod, mod_stride, drop_p, save, mean, want_mean)
+            x, saved, out_mean = self._block_forward(bp, x, skip, mod, mod_stride, drop_p, save, mean, want_mean, seed_t)
             if bp.kind == "enc":
                 skips.append(x)
                 means.append(out_mean)
@@ -484,7 +509,8 @@ class DenoiserEngine:
         return mean
 
     def _block_forward(self, bp: BlockPlan, xin: Tensor, skip: Tensor | None, mod: Tensor, mod_stride: int,
-                       drop_p: float, save: bool, skip_mean: Tensor | None = None, want_mean: bool = False):
+                       drop_p: float, save: bool, skip_mean: Tensor | None = None, want_mean: bool = False,
+                       seed_t: Tensor | None = None):
         """Returns (block output, tensors saved for backward, spatial mean of the output per (image, channel) or None)."""
         S: dict = {}
         B, Hin, Win, _ = xin.shape
@@ -517,7 +543,8 @@ class DenoiserEngine:
         wa, wb = ops.mp_add_coeffs(bp.add_t)
         raw = torch.empty((x.shape[0], x.shape[1], x.shape[2], bp.cout), device=x.device, dtype=BF16) if save else None
         h = ops.conv2d(a, bp.w["conv_3x3_1"].fwd, 3, bp.cout, epi=EPI_MODSILU, mod=mod, mod_off=bp.col0,
-                       mod_stride=mod_stride, drop_p=drop_p, seed=0x5EED0000 + bp.index, seed_ptr=self.step_counter, raw=raw)
+                       mod_stride=mod_stride, drop_p=drop_p, seed=0x5EED0000 + bp.index,
+                       seed_ptr=seed_t if seed_t is not None else self.step_counter, raw=raw)
         out, out_mean = self._conv_with_mean(h, bp.w["conv_3x3_2"].fwd, 3, bp.cout, want_mean and not bp.attn, epi=EPI_AXPBY,
                                              alpha=wb, beta=wa, res=xr)
         if save:
@@ -553,12 +580,17 @@ class DenoiserEngine:
         assert units[0][1] == self.bank._ghat_flat.numel()
         return units
 
-    def backward(self, ctx: dict, g_D: Tensor, *, need_g_emb: bool = True):
+    def backward(self, ctx: dict, g_D: Tensor, *, need_g_emb: bool = True, defer: bool = False):
         """Adjoint of `forward`. Fills every WeightSlot.grad, returns (g_emb, scalar_grads).
 
         scalar_grads: fp32 tensor [n_blocks + 1] = d(block gains..., gain_out).
         With `self.grad_sync` set (parallel.DistributedEDM) the g_hat regions are handed to the gradient all-reduce
         as soon as their block is done, so the exchange overlaps the rest of this backward.
+        `defer`: accumulate into g_hat / the scalar gradients only and return (g_emb, None): no Jacobian, no exchange.
+        The weight-norm Jacobian is linear in g_hat and the weights do not move between the micro-batches of one
+        optimiser step (the forced re-normalisation of an already normalised weight is the identity up to fp32
+        rounding), so J(sum g_hat) == sum J(g_hat): one Jacobian launch and one exchange per step instead of one per
+        micro-batch (SURVEY.md §8e "with accumulation reduce only on the last micro-batch").
         """
         m = self.m
         ops.check(g_D, F32, "grad of denoised_image")
@@ -566,16 +598,15 @@ class DenoiserEngine:
         dev = g_D.device
         sigma = ctx["sigma"]
         nb = len(self.blocks)
-        if self._sg is None or self._sg.device != dev:
-            self._sg = torch.zeros(nb + 1, device=dev, dtype=F32)
-        sg = self._sg
-        sg.zero_()
-        sync = self.grad_sync
+        sg = self.bank._ghat_flat[:nb + 1]          # 0-d gradients: front of the flat g_hat buffer (see _build_plan)
+        sync = None if defer else self.grad_sync
         if sync is not None:
             sync.backward_started()
-        # ONE memset for every dL/dw_hat of the network; all weight-gradient kernels then accumulate (split-K partial
-        # sums via TMA reduce-add / atomics) instead of zeroing their own slice with 70+ small memsets
-        self.bank._ghat_flat.zero_()
+        if self._accum == 0:
+            # ONE memset for every dL/dw_hat of the network (and the 0-d gradients); all weight-gradient kernels then
+            # accumulate (split-K partial sums via TMA reduce-add / atomics) instead of zeroing their own slice with
+            # 70+ small memsets
+            self.bank._ghat_flat.zero_()
         g = ops.conv_out_backward(g_D, ctx["f_raw"], ctx["x_last"], self.s_out.fwd, m.gain_out, sigma,
                                   float(m.sigma_data), self.s_out.ghat, sg[nb:])
         d_mod = torch.zeros((B, self.n_mod), device=dev, dtype=F32)
@@ -586,25 +617,35 @@ class DenoiserEngine:
                 sync.unit_done()
         # conv_in weight gradient (its input is the image: no data gradient needed)
         ops.conv2d_wgrad(g, ctx["xcol"], self.s_in.ghat, 1, accumulate=True)
-        # modulation adjoint: d_mod -> block gains, embed weights, embedding
-        d_lin = ops.mod_finish_backward(ctx["lin"], d_mod, self.gain_ptrs, self.blk_start, sg, nb)
-        emb = ctx["emb"]
-        E = emb.shape[1]
-        N = self.n_mod
-        g_emb = None
-        if need_g_emb:
-            g_emb = torch.empty((B, E), device=dev, dtype=F32)
-            ops.sgemm(d_lin, self.w_embed_all, g_emb, B, E, N, N, E, E, False, False)
-        first = self.embed_slots[0]
-        gh_all = self.bank._ghat_flat[first.ghat.storage_offset():first.ghat.storage_offset() + N * E].view(N, E)
-        ops.sgemm(d_lin, emb, gh_all, N, E, B, N, E, E, True, False)
+        g_emb = self._modulation_backward(ctx, d_mod, sg, need_g_emb)
+        if defer:
+            self._accum += 1
+            return g_emb, None
+        self._accum = 0
         if sync is not None:
             sync.unit_done()                 # trailing unit: embed weights, conv_in, conv_out
             sync.before_weight_jacobian()
         self.bank.backward()
-        if sync is not None:
-            sync.reduce_scalars(sg)
+        if self._sg_alive:
+            sg = sg.clone()      # 0-d `.grad`s handed out by an earlier backward still alias the buffer: do not share it
         return g_emb, sg
+
+    def _modulation_backward(self, ctx: dict, d_mod: Tensor, sg: Tensor, need_g_emb: bool):
+        """Adjoint of `m = embed(emb) * gain + 1` for every block at once: d_mod -> block gains (into sg), the embed
+        weights' dL/dw_hat (added to the flat g_hat buffer) and the embedding gradient (returned)."""
+        nb = len(self.blocks)
+        d_lin = ops.mod_finish_backward(ctx["lin"], d_mod, self.gain_ptrs, self.blk_start, sg, nb)
+        emb = ctx["emb"]
+        B, E = emb.shape
+        N = self.n_mod
+        g_emb = None
+        if need_g_emb:
+            g_emb = torch.empty((B, E), device=emb.device, dtype=F32)
+            ops.sgemm(d_lin, self.w_embed_all, g_emb, B, E, N, N, E, E, False, False)
+        first = self.embed_slots[0]
+        gh_all = self.bank._ghat_flat[first.ghat.storage_offset():first.ghat.storage_offset() + N * E].view(N, E)
+        ops.sgemm(d_lin, emb, gh_all, N, E, B, N, E, E, True, False, 1.0, 1.0)   # += : g_hat was zeroed by the memset
+        return g_emb
 
     def _take_g_in(self, bp: BlockPlan, pending: dict, shape, dev):
         """Buffer receiving the gradient w.r.t. this block's input. If the input is also a skip source whose
@@ -642,7 +683,7 @@ class DenoiserEngine:
         # (incl. the d_mod reduction) runs in the epilogue of conv2's data gradient
         g_raw = ops.conv2d(g_mid, w2.dgrad, 3, bp.cout, epi=EPI_MODSILU_BWD, alpha=wb, aux=S["raw"], mod=ctx["mod"],
                            mod_off=bp.col0, d_mod=d_mod, drop_p=ctx["drop_p"], seed=0x5EED0000 + bp.index,
-                           seed_ptr=self.step_counter)
+                           seed_ptr=ctx.get("seed", self.step_counter))
         ops.conv2d_wgrad(g_mid, S["h"], w2.ghat, 3, alpha=wb, accumulate=True)
         ops.conv2d_wgrad(g_raw, S["a"], w1.ghat, 3, accumulate=True)
         x = S["x"]
@@ -740,8 +781,15 @@ class DenoiserEngine:
     def begin_backward(self) -> None:
         """See WeightBank.begin_backward; also protects the scalar-gradient buffer."""
         self.bank.begin_backward()
-        if self._sg is not None and (self.m.gain_out.grad is not None or any(bp.gain.grad is not None for bp in self.blocks)):
-            self._sg = None
+        scalars = [bp.gain for bp in self.blocks] + [self.m.gain_out]
+        self._sg_alive = any(p.grad is not None for p in scalars)
+        if self._sg_alive and self._accum == 0:
+            # plain autograd accumulation (no zero_grad since the last hand-out): the 0-d `.grad`s may alias the front of
+            # the g_hat buffer, which this backward is about to clear
+            with torch.no_grad():
+                for p in scalars:
+                    if p.grad is not None:
+                        p.grad = p.grad.clone()
 
     def grads_by_param(self, sg: Tensor) -> dict[int, Tensor]:
         """id(param) -> a NEW view object into the bank's flat gradient buffer / the scalar gradient vector."""

@@ -27,17 +27,27 @@ def graphs_enabled() -> bool:
 
 
 class GraphedTrainStep:
-    """`step = GraphedTrainStep(model, optimizer, example_batch[, ddp]); loss = step(batch)`.
+    """`step = GraphedTrainStep(model, optimizer, example_batch[, ddp][, accumulate=k]); loss = step(batch)`.
 
-    `batch` = (clean_image (B,C,H,W) fp32, class_label (B,) int64), host (pinned) or device tensors of the example's
-    shapes; they are copied into static device buffers. Returns the static loss tensor of shape (1,) (overwritten by
-    the next call). Falls back to the eager step when capture is disabled (TEDM_CUDA_GRAPHS=0) or fails.
+    `batch` = (clean_image (k*B,C,H,W) fp32, class_label (k*B,) int64), host (pinned) or device tensors of the example's
+    shapes; they are copied into static device buffers. With `accumulate=k` (Lightning's `accumulate_grad_batches`,
+    imagenet.yaml:7) the batch is cut into k micro-batches of B whose gradients are summed (loss/k each, like Lightning)
+    with ONE gradient exchange and ONE weight-norm Jacobian, on the last micro-batch. Returns the static loss tensor of
+    shape (1,) (mean over the micro-batches; overwritten by the next call). Falls back to the eager step when capture is
+    disabled (TEDM_CUDA_GRAPHS=0) or fails.
+
+    The warm-up that precedes the capture runs forward + backward only (no optimiser step): parameters move only
+    through the training-mode forced weight normalisation (networks.py:32-34), exactly as in any training forward;
+    Adam moments, EMA and `current_step` are untouched.
     """
 
-    def __init__(self, model, optimizer, example_batch, ddp=None, warmup: int = 2):
+    def __init__(self, model, optimizer, example_batch, ddp=None, warmup: int = 2, accumulate: int = 1):
         self.model, self.opt, self.ddp = model, optimizer, ddp
         dev = next(model.parameters()).device
         x, y = example_batch
+        if accumulate < 1 or x.shape[0] % accumulate != 0:
+            raise ValueError(f"batch of {x.shape[0]} cannot be cut into {accumulate} micro-batches")
+        self.accumulate = accumulate
         self.x = torch.empty(x.shape, device=dev, dtype=torch.float32)
         self.y = torch.empty(y.shape, device=dev, dtype=y.dtype)
         self.x.copy_(x)
@@ -57,11 +67,22 @@ class GraphedTrainStep:
 
     def _fwd_bwd(self) -> Tensor:
         self.opt.zero_grad(set_to_none=True)
-        loss = self.model.training_step((self.x, self.y), 0)
-        loss.backward()
+        k = self.accumulate
+        if k == 1:
+            loss = self.model.training_step((self.x, self.y), 0)
+            loss.backward()
+            total = loss
+        else:
+            total = None
+            mb = self.x.shape[0] // k
+            for j in range(k):
+                with self.model.denoiser.accumulate_grads(j < k - 1):
+                    loss = self.model.training_step((self.x[j * mb:(j + 1) * mb], self.y[j * mb:(j + 1) * mb]), j) / k
+                    loss.backward()
+                total = loss.detach() if total is None else total + loss.detach()
         if self.ddp is not None:
             self.ddp.finish_backward()
-        return loss
+        return total
 
     def _capture(self) -> None:
         cur = torch.cuda.current_stream()
@@ -70,7 +91,6 @@ class GraphedTrainStep:
         with torch.cuda.stream(side):
             for _ in range(self._warmup):     # builds descriptor tables / gradient buffers outside the capture
                 self._fwd_bwd()
-                self.opt.step()
         cur.wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()

@@ -13,6 +13,7 @@ CPU path: CPU tensors raise.
 """
 from __future__ import annotations
 
+import contextlib
 import math
 
 import numpy as np
@@ -472,10 +473,13 @@ class _DenoiserFn(torch.autograd.Function):
         if ctx.saved is None:
             raise RuntimeError("tinyedm_b200.Denoiser: backward through the same forward twice is not supported")
         eng.begin_backward()     # gradient buffers handed out earlier and still alive are not overwritten
-        g_emb, sg = eng.backward(ctx.saved, g_D.float().contiguous(), need_g_emb=ctx.needs_input_grad[2])
+        g_emb, sg = eng.backward(ctx.saved, g_D.float().contiguous(), need_g_emb=ctx.needs_input_grad[2],
+                                 defer=eng.defer_grads)
+        ctx.saved = None
+        if sg is None:           # gradient accumulation: this micro-batch was only summed into g_hat (engine.backward)
+            return (None, None, g_emb, None) + (None,) * len(ctx.params)
         by_param = eng.grads_by_param(sg)
         grads = tuple(by_param[id(p)] if p.requires_grad else None for p in ctx.params)
-        ctx.saved = None
         return (None, None, g_emb, None) + grads
 
 
@@ -544,6 +548,19 @@ class Denoiser(nn.Module):
         eng = self.engine
         eng._ensure_device(torch.device(device))
         eng.bank.prepare(self.training)
+
+    @contextlib.contextmanager
+    def accumulate_grads(self, enabled: bool = True):
+        """Backwards inside this context only add to the flat dL/dw_hat buffer; the first backward after it hands out
+        the gradients of the whole sum (Lightning's `accumulate_grad_batches`, imagenet.yaml:7). Parameter `.grad`s of
+        the denoiser stay None inside the context."""
+        eng = self.engine
+        old = eng.defer_grads
+        eng.defer_grads = bool(enabled) or old
+        try:
+            yield
+        finally:
+            eng.defer_grads = old
 
     def __getstate__(self):  # the engine holds device buffers and ctypes tables: rebuild lazily after copy/unpickle
         state = self.__dict__.copy()

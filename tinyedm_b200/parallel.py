@@ -10,13 +10,16 @@ autograd hooks). Here the engine owns the backward, so the exchange is planned i
 * the engine completes blocks in reverse order and the bank lays g_hat out in forward order, so finished regions
   grow from the END of one flat buffer: buckets are contiguous slices, launched on a side stream as soon as their
   last block is done, overlapping the remaining dgrad/wgrad work;
-* the few tensors produced outside the Denoiser adjoint (embedding / uncertainty weights, 0-d gains) are reduced
-  in one small trailing message.
+* the gradients of the 0-d parameters (block gains, gain_out) sit at the front of the same flat buffer and ride in its
+  last message; the last unit to complete (embed weights, conv_in, conv_out) travels alone so that the only message
+  with nothing left to hide under is small; the few tensors produced outside the Denoiser adjoint (embedding /
+  uncertainty weights) follow in one small message (`finish_backward`).
 
 Sampling needs no collective: rank r takes a contiguous slice of the batch (`shard_slice`).
 """
 from __future__ import annotations
 
+import contextlib
 from dataclasses import dataclass
 
 import torch
@@ -37,9 +40,11 @@ class Bucket:
     ready_after: int  # index (in BACKWARD completion order) of the unit whose completion makes the bucket ready
 
 
-def plan_buckets(unit_ranges: list[tuple[int, int]], bucket_elems: int) -> list[Bucket]:
+def plan_buckets(unit_ranges: list[tuple[int, int]], bucket_elems: int, lone_tail: bool = False) -> list[Bucket]:
     """unit_ranges[i] = (start, end) of the i-th unit to COMPLETE during backward; units must tile a contiguous region
-    from its end towards its start. Greedy: close a bucket once it holds >= bucket_elems."""
+    from its end towards its start. Greedy: close a bucket once it holds >= bucket_elems. `lone_tail`: the last unit
+    travels alone (a bucket is closed right before it), so the only message with no compute left to hide under is as
+    small as the plan allows."""
     buckets: list[Bucket] = []
     cur_end = None      # end of the bucket being filled
     prev_start = None   # start of the most recent unit: the next one must end exactly there
@@ -52,7 +57,7 @@ def plan_buckets(unit_ranges: list[tuple[int, int]], bucket_elems: int) -> list[
         if cur_end is None:
             cur_end = e
         cur_start = prev_start = s
-        if cur_end - cur_start >= bucket_elems:
+        if cur_end - cur_start >= bucket_elems or (lone_tail and i == len(unit_ranges) - 2):
             buckets.append(Bucket(cur_start, cur_end, i))
             cur_end = None
     if cur_end is not None:
@@ -118,13 +123,16 @@ class DistributedEDM:
         if broadcast:
             for t in list(model.parameters()) + list(model.buffers()):
                 dist.broadcast(t.data, src=0, group=group)
-            eng.bank.invalidate()
+            from .engine import bump_weights_epoch
+            bump_weights_epoch()      # `.data` writes bump no version: every bank (denoiser, embedding, head) is stale
 
     # ---- engine callbacks (see DenoiserEngine.backward) ----
     def _ensure_plan(self):
         if self._plan is None:
             units = self._eng.ghat_units_backward_order()
-            self._plan = plan_buckets([u for u in units], self.bucket_elems)
+            # the trailing unit (embed weights of all blocks, conv_in, conv_out and the 0-d gradients at the front of the
+            # buffer) completes when nothing is left to overlap with: it travels alone, everything before it is in flight
+            self._plan = plan_buckets([u for u in units], self.bucket_elems, lone_tail=True)
         return self._plan
 
     def backward_started(self) -> None:
@@ -147,9 +155,15 @@ class DistributedEDM:
         assert self._next_bucket == len(self._plan), "a g_hat bucket was never launched"
         self.reducer.wait()
 
-    def reduce_scalars(self, sg: torch.Tensor) -> None:
-        self.reducer.launch(sg)
-        self.reducer.wait()
+    # ---- gradient accumulation ----
+    @contextlib.contextmanager
+    def no_sync(self, enabled: bool = True):
+        """DDP's `no_sync()` for this wrapper (Lightning enters it for all but the last micro-batch when
+        `accumulate_grad_batches > 1`, imagenet.yaml:7): backwards inside the context only add to the local flat g_hat
+        buffer; the first backward outside it exchanges the SUM once and hands out the gradients. Call
+        `finish_backward()` only after that last backward."""
+        with self.model.denoiser.accumulate_grads(enabled):
+            yield
 
     # ---- after loss.backward() ----
     def finish_backward(self) -> None:

@@ -41,6 +41,9 @@ def swap_tensors(tensor1, tensor2):
     tmp.copy_(tensor1)
     tensor1.copy_(tensor2)
     tensor2.copy_(tmp)
+    # `param.data` writes do not bump `param._version`: tell the weight banks their cached normalised weights are stale
+    from .engine import bump_weights_epoch
+    bump_weights_epoch()
 
 
 def _resolve(target: str):
