@@ -39,10 +39,17 @@ def load():
                 nets, solv = _load_one("networks"), _load_one("solvers")
             if nets is not None and solv is not None:
                 ref = types.SimpleNamespace(networks=nets, solvers=solv)
-        except Exception:  # noqa: BLE001 - stale bytecode (other interpreter): behave as absent
+        except Exception as e:  # noqa: BLE001 - stale bytecode (other interpreter): behave as absent
             ref = None
+            _cache["error"] = f"{type(e).__name__}: {e}"
         _cache["ref"] = ref
     return _cache["ref"]
+
+
+def load_error() -> str | None:
+    """Why `load()` returned None (None when the bytecode is simply absent)."""
+    load()
+    return _cache.get("error")
 
 
 def reference_edm_parts(cfg: dict):

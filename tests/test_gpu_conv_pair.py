@@ -123,16 +123,25 @@ def test_pair_wgrad_vs_torch_and_single(dev, B, H, W, Cin, Cout, ks):
     torch.manual_seed(B + Cin)
     x = torch.randn(B, H, W, Cin, device=dev).to(BF)
     g = torch.randn(B, H, W, Cout, device=dev).to(BF)
-    w0 = torch.zeros(Cout, Cin, ks, ks, device=dev, requires_grad=True)
-    (gw,) = torch.autograd.grad(F.conv2d(x.float().permute(0, 3, 1, 2), w0, padding="same"), w0, g.float().permute(0, 3, 1, 2))
+    K = B * H * W                      # contraction length of the weight gradient
+    big = K > 100_000
+    dt = torch.float64 if big else torch.float32     # the fp32 torch reference itself drifts at K ~ 10^5..10^6: use fp64 there
+    w0 = torch.zeros(Cout, Cin, ks, ks, device=dev, dtype=dt, requires_grad=True)
+    (gw,) = torch.autograd.grad(F.conv2d(x.to(dt).permute(0, 3, 1, 2), w0, padding="same"), w0, g.to(dt).permute(0, 3, 1, 2))
     ref = gw.permute(0, 2, 3, 1).reshape(Cout, ks * ks, Cin)
+    # fp32 accumulation in the tensor core (products exact, running sum rounded once per k-block of 16 pixels) plus fp32
+    # split-K reduce-adds: the error grows with the contraction length. 1e-4 up to K = 50 000, then 2e-9 per pixel
+    # (measured 1.7e-4 at K = 262 144 and 3.9e-4 at K = 720 896 against fp64)
+    tol = max(1e-4, 2e-9 * K)
     for acc in (False, True):
         dw = torch.full((Cout, ks * ks, Cin), 3.0, device=dev)
         ops.conv2d_wgrad(g, x, dw, ks, alpha=0.5, accumulate=acc)                 # CTA-pair kernel (TMA reduce-add)
-        assert rel(dw, 0.5 * ref + (3.0 if acc else 0.0)) < 1e-4
+        assert rel(dw, 0.5 * ref + (3.0 if acc else 0.0)) < tol
+        if big and acc:
+            continue                       # the single-CTA comparison once per big case is enough
         dws = torch.full((Cout, ks * ks, Cin), 3.0, device=dev)
         ops.conv2d_wgrad(g, x, dws, ks, alpha=0.5, accumulate=acc, splits=-1)      # single-CTA kernel (vector atomics)
-        assert rel(dw, dws) < 1e-4
+        assert rel(dw, dws) < 2 * tol
 
 
 @pytest.mark.parametrize("B,H,W,Cin,C1,C2", [(40, 32, 32, 256, 256, 256), (150, 8, 8, 256, 256, 256), (256, 32, 32, 256, 256, 256),

@@ -197,45 +197,80 @@ mod_finish_bwd_kernel(const float* __restrict__ lin, const float* __restrict__ d
 }
 
 // ------------------------------------------------------------------------------------------------
-// ScaleLong MLP (per batch row)
+// ScaleLong MLP (networks.py:106-118): gain = sigmoid(W2 mp_silu(W1 [mean, 1])), R = C/16 hidden units
 // ------------------------------------------------------------------------------------------------
+// The arithmetic is ~10 MFLOP; what costs time is reading the two weight matrices (up to 2 x 148 KB, from L2) with
+// enough loads in flight. A CTA therefore owns kSlG batch rows (every weight element it loads is used kSlG times), and
+// each phase walks the weights in the direction that is contiguous in memory: W1 [R][C+1] row by row with the lanes
+// along c, W2 [C][R] one 16-byte-vectorised row per thread (forward) or one row per warp iteration with the lanes along
+// j (backward). The first version (one CTA per batch row, strided W2 reads) took 73 / 145 us forward / backward on the
+// ImageNet-latent shapes (C = 768, B = 64).
+constexpr int kSlG = 4;
+
 __global__ void __launch_bounds__(256)
 scalelong_fwd_kernel(const ScaleLongArgs a) {
   pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
   pdl_wait();      // ... and this one was: everything below needs its predecessors complete
-  extern __shared__ float sm[];  // aug[C+1], h[R]
+  extern __shared__ float sm[];  // aug[G][C+1], h[G][R]
+  const int C = a.C, R = a.R, C1 = a.C + 1;
   float* aug = sm;
-  float* h = sm + a.C + 1;
-  const int b = blockIdx.x;
-  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-    const float v = a.mean[(size_t)b * a.C + c];
-    aug[c] = v;
-    a.aug_out[(size_t)b * (a.C + 1) + c] = v;
-  }
-  if (threadIdx.x == 0) {
-    aug[a.C] = 1.0f;
-    a.aug_out[(size_t)b * (a.C + 1) + a.C] = 1.0f;
+  float* h = sm + kSlG * C1;
+  const int b0 = blockIdx.x * kSlG;
+  for (int i = threadIdx.x; i < kSlG * C1; i += blockDim.x) {
+    const int g = i / C1, c = i - g * C1;
+    const int b = b0 + g;
+    float v = 0.f;
+    if (b < a.B) {
+      v = c < C ? a.mean[(size_t)b * C + c] : 1.0f;
+      a.aug_out[(size_t)b * C1 + c] = v;
+    }
+    aug[i] = v;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int j = warp; j < a.R; j += blockDim.x / 32) {
-    const float* w = a.w1 + (size_t)j * (a.C + 1);
-    float acc = 0.f;
-    for (int c = lane; c <= a.C; c += 32) acc += w[c] * aug[c];
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      a.h_pre[(size_t)b * a.R + j] = acc;
-      const float hv = mp_silu_f(acc);
-      h[j] = hv;
-      a.h_out[(size_t)b * a.R + j] = hv;
+  for (int j = warp; j < R; j += 8) {
+    const float* w = a.w1 + (size_t)j * C1;
+    float acc[kSlG] = {};
+#pragma unroll 4
+    for (int c = lane; c < C1; c += 32) {
+      const float wv = w[c];
+#pragma unroll
+      for (int g = 0; g < kSlG; ++g) acc[g] = fmaf(wv, aug[g * C1 + c], acc[g]);
+    }
+#pragma unroll
+    for (int g = 0; g < kSlG; ++g) {
+      const float t = warp_sum(acc[g]);
+      if (lane == 0 && b0 + g < a.B) {
+        a.h_pre[(size_t)(b0 + g) * R + j] = t;
+        const float hv = mp_silu_f(t);
+        h[g * R + j] = hv;
+        a.h_out[(size_t)(b0 + g) * R + j] = hv;
+      }
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-    const float* w = a.w2 + (size_t)c * a.R;
-    float acc = 0.f;
-    for (int j = 0; j < a.R; ++j) acc += w[j] * h[j];
-    a.gain[(size_t)b * a.C + c] = 1.0f / (1.0f + __expf(-acc));
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float* w = a.w2 + (size_t)c * R;
+    float acc[kSlG] = {};
+    if ((R & 3) == 0) {
+      for (int j = 0; j < R; j += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(w + j);
+#pragma unroll
+        for (int g = 0; g < kSlG; ++g) {
+          const float* hg = h + g * R + j;
+          acc[g] += wv.x * hg[0] + wv.y * hg[1] + wv.z * hg[2] + wv.w * hg[3];
+        }
+      }
+    } else {
+      for (int j = 0; j < R; ++j) {
+        const float wv = w[j];
+#pragma unroll
+        for (int g = 0; g < kSlG; ++g) acc[g] = fmaf(wv, h[g * R + j], acc[g]);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < kSlG; ++g)
+      if (b0 + g < a.B) a.gain[(size_t)(b0 + g) * C + c] = 1.0f / (1.0f + __expf(-acc[g]));
   }
 }
 
@@ -243,61 +278,130 @@ __global__ void __launch_bounds__(256)
 scalelong_bwd_kernel(const ScaleLongBwdArgs a) {
   pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
   pdl_wait();      // ... and this one was: everything below needs its predecessors complete
-  extern __shared__ float sm[];  // dp2[C], dhp[R]
+  extern __shared__ float sm[];  // dp2[G][C], part[8][G][R], dhp[G][R]
+  const int C = a.C, R = a.R, C1 = a.C + 1;
   float* dp2 = sm;
-  float* dhp = sm + a.C;
-  const int b = blockIdx.x;
-  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-    const float g = a.gain[(size_t)b * a.C + c];
-    // gain = sigmoid(pre2): d pre2 = d gain * g (1 - g); the split conv epilogue already delivers (d gain) * g
-    const float v = a.d_gain[(size_t)b * a.C + c] * (a.d_gain_times_gain ? 1.0f : g) * (1.0f - g);
-    dp2[c] = v;
-    a.d_pre2[(size_t)b * a.C + c] = v;
+  float* part = sm + kSlG * C;
+  float* dhp = part + 8 * kSlG * R;
+  const int b0 = blockIdx.x * kSlG;
+  for (int i = threadIdx.x; i < kSlG * C; i += blockDim.x) {
+    const int g = i / C, c = i - g * C;
+    const int b = b0 + g;
+    float v = 0.f;
+    if (b < a.B) {
+      const float gn = a.gain[(size_t)b * C + c];
+      // gain = sigmoid(pre2): d pre2 = d gain * g (1 - g); the split conv epilogue already delivers (d gain) * g
+      v = a.d_gain[(size_t)b * C + c] * (a.d_gain_times_gain ? 1.0f : gn) * (1.0f - gn);
+      a.d_pre2[(size_t)b * C + c] = v;
+    }
+    dp2[i] = v;
   }
   __syncthreads();
+  // d h[g][j] = sum_c dp2[g][c] W2[c][j]: warp w takes c = w, w+8, ...; the lanes run along j (one contiguous W2 row)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int j = warp; j < a.R; j += blockDim.x / 32) {
-    float acc = 0.f;
-    for (int c = lane; c < a.C; c += 32) acc += dp2[c] * a.w2[(size_t)c * a.R + j];
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      const float v = acc * mp_silu_grad_f(a.h_pre[(size_t)b * a.R + j]);
-      dhp[j] = v;
-      a.d_hpre[(size_t)b * a.R + j] = v;
+  for (int j0 = 0; j0 < R; j0 += 64) {
+    float acc[kSlG][2] = {};
+    const int ja = j0 + lane, jb = j0 + 32 + lane;
+#pragma unroll 4
+    for (int c = warp; c < C; c += 8) {
+      const float* w = a.w2 + (size_t)c * R;
+      const float wa = ja < R ? w[ja] : 0.f;
+      const float wb = jb < R ? w[jb] : 0.f;
+#pragma unroll
+      for (int g = 0; g < kSlG; ++g) {
+        const float d = dp2[g * C + c];
+        acc[g][0] = fmaf(d, wa, acc[g][0]);
+        acc[g][1] = fmaf(d, wb, acc[g][1]);
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < kSlG; ++g) {
+      if (ja < R) part[(warp * kSlG + g) * R + ja] = acc[g][0];
+      if (jb < R) part[(warp * kSlG + g) * R + jb] = acc[g][1];
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-    float acc = 0.f;
-    for (int j = 0; j < a.R; ++j) acc += dhp[j] * a.w1[(size_t)j * (a.C + 1) + c];
-    a.d_mean[(size_t)b * a.C + c] = acc;
+  for (int i = threadIdx.x; i < kSlG * R; i += blockDim.x) {
+    const int g = i / R, j = i - g * R;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[(w * kSlG + g) * R + j];
+    float v = 0.f;
+    if (b0 + g < a.B) {
+      v = t * mp_silu_grad_f(a.h_pre[(size_t)(b0 + g) * R + j]);
+      a.d_hpre[(size_t)(b0 + g) * R + j] = v;
+    }
+    dhp[i] = v;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc[kSlG] = {};
+#pragma unroll 4
+    for (int j = 0; j < R; ++j) {
+      const float wv = a.w1[(size_t)j * C1 + c];
+#pragma unroll
+      for (int g = 0; g < kSlG; ++g) acc[g] = fmaf(dhp[g * R + j], wv, acc[g]);
+    }
+#pragma unroll
+    for (int g = 0; g < kSlG; ++g)
+      if (b0 + g < a.B) a.d_mean[(size_t)(b0 + g) * C + c] = acc[g];
   }
 }
 
-// Weight gradients of both ScaleLong layers in ONE launch (they were two split-K sgemm launches + two memsets per skip
-// block): dW2[c][j] += sum_b d_pre2[b][c] h[b][j]  (C x R),  dW1[j][c] += sum_b d_hpre[b][j] aug[b][c]  (R x (C+1)).
-// One thread per output element, blockIdx.y splits the batch; results are accumulated atomically (dw zeroed by the caller).
+// Weight gradients of both ScaleLong layers in ONE launch: dW2[c][j] += sum_b d_pre2[b][c] h[b][j]  (C x R),
+// dW1[j][c] += sum_b d_hpre[b][j] aug[b][c]  (R x (C+1)). A CTA owns a 32-wide c tile of one of the two matrices (all R
+// hidden units) and walks the batch in chunks of 32 rows staged through shared memory (coalesced loads, each operand
+// element read once per CTA); blockIdx.y splits the batch. Results are added atomically (the flat g_hat buffer is
+// zeroed once per step and may already hold earlier micro-batches).
+constexpr int kSlWgJ = 8;   // hidden units per thread: R <= 64
 __global__ void __launch_bounds__(256)
 scalelong_wgrad_kernel(const float* __restrict__ d_pre2, const float* __restrict__ h, const float* __restrict__ d_hpre,
                        const float* __restrict__ aug, float* __restrict__ dw2, float* __restrict__ dw1, int B, int C, int R) {
   pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
   pdl_wait();      // ... and this one was: everything below needs its predecessors complete
-  const int n2 = C * R, n1 = R * (C + 1);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n1 + n2) return;
-  const int chunk = (B + gridDim.y - 1) / gridDim.y;
-  const int b0 = blockIdx.y * chunk;
-  const int b1 = b0 + chunk < B ? b0 + chunk : B;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  if (i < n2) {
-    const int c = i / R, j = i - c * R;
-    for (int b = b0; b < b1; ++b) acc[b & 3] += d_pre2[(size_t)b * C + c] * h[(size_t)b * R + j];
-    atomicAdd(dw2 + i, (acc[0] + acc[1]) + (acc[2] + acc[3]));
-  } else {
-    const int k = i - n2;
-    const int j = k / (C + 1), c = k - j * (C + 1);
-    for (int b = b0; b < b1; ++b) acc[b & 3] += d_hpre[(size_t)b * R + j] * aug[(size_t)b * (C + 1) + c];
-    atomicAdd(dw1 + k, (acc[0] + acc[1]) + (acc[2] + acc[3]));
+  extern __shared__ float sm[];   // A[32][33] (batch row, c), Bm[32][R] (batch row, j)
+  float* As = sm;
+  float* Bs = sm + 32 * 33;
+  const int C1 = C + 1;
+  const int tiles2 = (C + 31) / 32;
+  const bool second = (int)blockIdx.x < tiles2;        // this CTA: a tile of dW2, else a tile of dW1
+  const int c0 = (second ? (int)blockIdx.x : (int)blockIdx.x - tiles2) * 32;
+  const int width = second ? C : C1;                     // row length of the batch-major operand holding the c axis
+  const float* Ag = second ? d_pre2 : aug;
+  const float* Bg = second ? h : d_hpre;
+  const int chunk = ((B + gridDim.y - 1) / gridDim.y + 31) / 32 * 32;
+  const int b_begin = blockIdx.y * chunk;
+  const int b_end = min(B, b_begin + chunk);
+  const int cl = threadIdx.x & 31, jg = threadIdx.x >> 5;
+  float acc[kSlWgJ] = {};
+  for (int bb = b_begin; bb < b_end; bb += 32) {
+    __syncthreads();
+#pragma unroll
+    for (int r = jg; r < 32; r += 8) {
+      const int b = bb + r, c = c0 + cl;
+      As[r * 33 + cl] = (b < b_end && c < width) ? Ag[(size_t)b * width + c] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 32 * R; i += 256) {
+      const int r = i / R, j = i - r * R;
+      Bs[i] = (bb + r < b_end) ? Bg[(size_t)(bb + r) * R + j] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      const float av = As[r * 33 + cl];
+#pragma unroll
+      for (int t = 0; t < kSlWgJ; ++t) {
+        const int j = jg + 8 * t;
+        if (j < R) acc[t] = fmaf(av, Bs[r * R + j], acc[t]);
+      }
+    }
+  }
+  const int c = c0 + cl;
+  if (c >= width) return;
+#pragma unroll
+  for (int t = 0; t < kSlWgJ; ++t) {
+    const int j = jg + 8 * t;
+    if (j < R) atomicAdd(second ? dw2 + (size_t)c * R + j : dw1 + (size_t)j * C1 + c, acc[t]);
   }
 }
 
@@ -928,21 +1032,27 @@ int mod_finish_backward(const float* lin, const float* dm, const float* const* g
   return 0;
 }
 int scalelong_forward(const ScaleLongArgs& a, cudaStream_t stream) {
-  launch_pdl(scalelong_fwd_kernel, a.B, 256, (a.C + 1 + a.R) * sizeof(float), stream, a);
+  if (a.B <= 0) return 0;
+  const size_t smem = (size_t)kSlG * (a.C + 1 + a.R) * sizeof(float);
+  TEDM_CHECK(smem <= 48 * 1024, "scalelong: skip width %d too large", a.C);
+  launch_pdl(scalelong_fwd_kernel, (a.B + kSlG - 1) / kSlG, 256, smem, stream, a);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
 int scalelong_backward(const ScaleLongBwdArgs& a, cudaStream_t stream) {
-  launch_pdl(scalelong_bwd_kernel, a.B, 256, (a.C + a.R) * sizeof(float), stream, a);
+  if (a.B <= 0) return 0;
+  const size_t smem = (size_t)kSlG * (a.C + 9 * a.R) * sizeof(float);
+  TEDM_CHECK(smem <= 48 * 1024, "scalelong: skip width %d too large", a.C);
+  launch_pdl(scalelong_bwd_kernel, (a.B + kSlG - 1) / kSlG, 256, smem, stream, a);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
 int scalelong_wgrad(const float* d_pre2, const float* h, const float* d_hpre, const float* aug, float* dw2, float* dw1, int B,
                     int C, int R, cudaStream_t stream) {
   if (B <= 0) return 0;
-  const int n = C * R + R * (C + 1);
-  dim3 grid((n + 255) / 256, B >= 64 ? 8 : 1);
-  launch_pdl(scalelong_wgrad_kernel, grid, 256, 0, stream, d_pre2, h, d_hpre, aug, dw2, dw1, B, C, R);
+  TEDM_CHECK(R <= 8 * kSlWgJ, "scalelong: %d hidden units not supported (max %d)", R, 8 * kSlWgJ);
+  dim3 grid((C + 31) / 32 + (C + 1 + 31) / 32, B >= 128 ? 4 : (B >= 64 ? 2 : 1));
+  launch_pdl(scalelong_wgrad_kernel, grid, 256, (32 * 33 + 32 * R) * sizeof(float), stream, d_pre2, h, d_hpre, aug, dw2, dw1, B, C, R);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
