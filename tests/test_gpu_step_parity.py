@@ -56,21 +56,84 @@ def test_diffuse_kernel_vs_reference_golden(dev, golden):
 
 
 def test_diffuser_module_statistics_and_freshness(dev):
-    """`Diffuser.forward`: ln(sigma) ~ N(P_mean, P_std), noise ~ N(0, sigma^2) independent of the image, new draws on
-    every call, no gradient (edm.py:84 `@torch.no_grad`)."""
+    """`Diffuser.forward` (in-kernel Philox draws): ln(sigma) ~ N(P_mean, P_std), noise ~ N(0, sigma^2)
+    independent of the image, new draws on every call, no gradient (edm.py:84 `@torch.no_grad`), reproducible from
+    (seed, step)."""
     import tinyedm_b200 as T
     torch.manual_seed(123)
     diff = T.Diffuser(-1.2, 1.2)
     clean = torch.zeros(4096, 3, 8, 8, device=dev)
     noisy, sigma = diff(clean)
-    assert not noisy.requires_grad and sigma.shape == (4096,)
+    assert not noisy.requires_grad and sigma.shape == (4096,) and noisy.dtype == torch.float32
     ls = sigma.log()
     assert abs(float(ls.mean()) + 1.2) < 0.08 and abs(float(ls.std()) - 1.2) < 0.08
     z = noisy / sigma.view(-1, 1, 1, 1)                       # unit normal draws
     assert abs(float(z.mean())) < 5e-3 and abs(float(z.std()) - 1.0) < 5e-3
+    assert abs(float((z ** 3).mean())) < 2e-2 and abs(float((z ** 4).mean()) - 3.0) < 5e-2     # skewness 0, kurtosis 3
     assert abs(float((z[:, 0] * z[:, 1]).mean())) < 1e-2      # channels uncorrelated
+    assert abs(float((z[:-1] * z[1:]).mean())) < 1e-2         # images uncorrelated
+    assert abs(float((z[..., :-1] * z[..., 1:]).mean())) < 1e-2   # neighbouring pixels (they share a Philox call) uncorrelated
+    assert float(z.abs().max()) > 4.0                          # tails are there (786 432 draws)
     noisy2, sigma2 = diff(clean)
     assert not torch.equal(sigma, sigma2) and not torch.equal(noisy, noisy2)
+    diff.seed(diff._seed, 0)                                   # rewind: the same (seed, step) gives the same draws
+    noisy3, sigma3 = diff(clean)
+    assert torch.equal(noisy3, noisy) and torch.equal(sigma3, sigma)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(6, 3, 32, 32), (5, 1, 28, 28), (3, 4, 64, 64), (2, 3, 16, 16)])
+def test_fused_diffuser_equals_its_parts(dev, B, C, H, W):
+    """The fused kernel against the separate steps it replaces, on ITS OWN draws: noisy/sigma == edm.py:84-93 evaluated by
+    the oracle on (epsilon, n); the hand-over operand == tedm_conv_in_im2col(noisy, sigma) bit for bit; the Denoiser
+    consumes the hand-over (same output as when it gathers the patches itself)."""
+    import tinyedm_b200 as T
+    from tinyedm_b200 import ops
+    g = torch.Generator().manual_seed(B + H)
+    clean = (0.5 * torch.randn(B, C, H, W, generator=g)).clamp(-1, 1).to(dev)
+    diff = T.Diffuser(-0.4, 1.0)
+    diff._fuse_sigma_data = 0.5
+    diff.seed(1234567, 41)
+    noisy, sigma = diff(clean)
+    eps, noise = diff.draws(B, C * H * W, dev)
+    no, so = O.diffuse(clean.cpu(), eps.cpu(), noise.view(B, C, H, W).cpu(), -0.4, 1.0)
+    assert rel(sigma, so) < 1e-6 and rel(noisy, no) < 1e-6
+    n2, s2 = ops.diffuse(clean, eps, noise.view(B, C, H, W).contiguous(), -0.4, 1.0)     # the two-input kernel on the same draws
+    assert rel(noisy, n2) < 1e-6 and rel(sigma, s2) < 1e-6
+    xcol, sd, ptr = noisy._tedm_xcol
+    assert sd == 0.5 and ptr == sigma.data_ptr()
+    assert torch.equal(xcol, ops.conv_in_im2col(noisy, sigma, 0.5))
+
+
+def test_training_step_uses_the_fused_input_block_and_graph_replays_draw_fresh_noise(dev):
+    import tinyedm_b200 as T
+    from tinyedm_b200 import ops
+    model, _ = _small_edm(dev)
+    model.train()
+    assert model.diffuser._fuse_sigma_data == 0.5
+    g = torch.Generator().manual_seed(4)
+    clean = (0.5 * torch.randn(8, 3, 16, 16, generator=g)).clamp(-1, 1).to(dev)
+    labels = torch.randint(0, 5, (8,), generator=g).to(dev)
+    calls = []
+    orig = ops.conv_in_im2col
+    ops.conv_in_im2col = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    try:
+        model.diffuser.seed(9, 0)
+        l1 = float(model.training_step((clean, labels), 0))
+        assert not calls, "the engine re-gathered the patches although the diffuser handed them over"
+        # a caller-made noisy image (no hand-over) still works and gives the same loss for the same noise
+        noisy, sigma = model.diffuser(clean)          # step 2
+        del noisy._tedm_xcol
+        _, e = model.embedding(sigma, labels)
+        D = model.denoiser(noisy, sigma, e)
+        assert calls and torch.isfinite(D).all()
+    finally:
+        ops.conv_in_im2col = orig
+    opt = T.FusedAdamEMA(model.parameters(), lr=1e-4)
+    step = T.GraphedTrainStep(model, opt, (clean, labels), warmup=1)
+    assert step.graph is not None, step.error
+    losses = [float(step((clean, labels))) for _ in range(4)]
+    assert len({round(l, 6) for l in losses}) == 4, losses     # same batch, different sigma / noise on every replay
+    assert abs(losses[0] - l1) > 0
 
 
 def test_validation_step_vs_oracle(dev):
@@ -143,11 +206,10 @@ def test_gradient_accumulation_equals_one_big_batch(dev):
     k, mb = 3, 4
     clean = (0.5 * torch.randn(k * mb, 3, 16, 16, generator=g)).clamp(-1, 1).to(dev)
     labels = torch.randint(0, 5, (k * mb,), generator=g).to(dev)
-    state = torch.cuda.get_rng_state(dev)
 
     def run(deferred: bool):
         model.zero_grad(set_to_none=True)
-        torch.cuda.set_rng_state(state, dev)
+        model.diffuser.seed(5, 0)                # the same diffusion noise in every run
         for j in range(k):
             batch = (clean[j * mb:(j + 1) * mb], labels[j * mb:(j + 1) * mb])
             with model.denoiser.accumulate_grads(deferred and j < k - 1):

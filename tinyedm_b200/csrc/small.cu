@@ -948,6 +948,110 @@ __global__ void diffuse_kernel(const float* __restrict__ clean, const float* __r
 }
 
 // ------------------------------------------------------------------------------------------------
+// Diffuser.forward with in-kernel normal draws, fused with the Denoiser's input block
+// ------------------------------------------------------------------------------------------------
+// Reference: epsilon = randn(B); sigma = exp(P_mean + epsilon P_std); noisy = clean + randn_like(clean) sigma
+// (src/tinyedm/edm.py:84-93), then x = c_in noisy, ones channel, conv_in's 3x3 patch gather (networks.py:578-587):
+// two Philox launches, three elementwise launches and an image-sized round trip per tensor. Here ONE kernel draws both
+// normals with a counter-based Philox4x32-10 (key = seed; counter = (index / 4, stream tag, step)), so the value of
+// element e is a pure function of (seed, step, e): any thread may regenerate a neighbour's noise instead of waiting for
+// it, which is what lets the patch gather ride in the same pass. `step` lives on the device (incremented by the host
+// side per call, inside a CUDA graph too), so graph replays draw fresh noise.
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// the e-th standard normal of stream `tag` (0: image noise, 1: epsilon) at (seed, step): Box-Muller on two of the four
+// words of Philox call e / 4 (elements 4i..4i+3 share one call)
+__device__ __forceinline__ float philox_normal(unsigned long long e, uint32_t tag, unsigned long long seed,
+                                               unsigned long long step) {
+  const unsigned long long call = e >> 2;
+  const uint4 r = philox4x32_10((uint32_t)call, (uint32_t)(call >> 32) | (tag << 30), (uint32_t)step, (uint32_t)(step >> 32),
+                                (uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint32_t a = (e & 2) ? r.z : r.x, b = (e & 2) ? r.w : r.y;
+  const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);     // (0, 1)
+  const float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float rad = sqrtf(-2.0f * logf(u1));
+  float sn, cs;
+  sincospif(2.0f * u2, &sn, &cs);
+  return rad * ((e & 1) ? sn : cs);
+}
+
+// one thread per (pixel, group of 8 patch columns) exactly like conv_in_im2col_kernel; the g == 0 thread of a pixel also
+// writes the pixel's `noisy` values, the first thread of an image its sigma
+template <int CI>
+__global__ void __launch_bounds__(256)
+diffuse_philox_kernel(const float* __restrict__ clean, unsigned long long seed, const long long* __restrict__ step_ptr,
+                      float P_mean, float P_std, float sigma_data, float* __restrict__ noisy, float* __restrict__ sigma,
+                      __nv_bfloat16* __restrict__ xcol, int B, int Ci_rt, int H, int W) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (pixel, group of 8 k)
+  const long long total = (long long)B * H * W * 8;
+  if (idx >= total) return;
+  const unsigned long long step = (unsigned long long)*step_ptr;
+  const int Ci = CI > 0 ? CI : Ci_rt;
+  const int g = (int)(idx & 7);
+  const int pix = (int)(idx >> 3);
+  const int hw = H * W;
+  const int b = pix / hw, p = pix - b * hw;
+  const int h = p / W, w = p - h * W;
+  const float s = __expf(P_mean + philox_normal((unsigned long long)b, 1u, seed, step) * P_std);
+  const size_t img = (size_t)b * Ci * hw;
+  if (g == 0) {
+    if (p == 0) sigma[b] = s;
+    for (int ci = 0; ci < Ci; ++ci) {
+      const size_t e = img + (size_t)ci * hw + p;
+      noisy[e] = clean[e] + philox_normal(e, 0u, seed, step) * s;
+    }
+  }
+  if (xcol == nullptr) return;
+  const float c_in = rsqrtf(sigma_data * sigma_data + s * s);
+  const int cin = Ci + 1;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = g * 8 + i;
+    float val = 0.f;
+    if (k < 9 * cin) {
+      const int tap = k / cin, ci = k - tap * cin;
+      const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+        if (ci < Ci) {
+          const size_t e = img + (size_t)(ci * H + hh) * W + ww;
+          val = c_in * (clean[e] + philox_normal(e, 0u, seed, step) * s);   // the same fp32 value the owner of e stores
+        } else {
+          val = 1.0f;
+        }
+      }
+    }
+    v[i] = val;
+  }
+  uint4 o;
+  o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(xcol + (size_t)pix * 64 + g * 8) = o;
+}
+
+__global__ void __launch_bounds__(256)
+philox_draws_kernel(unsigned long long seed, const long long* __restrict__ step_ptr, float* __restrict__ eps,
+                    float* __restrict__ noise, int B, long long n) {
+  pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
+  pdl_wait();      // ... and this one was: everything below needs its predecessors complete
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long step = (unsigned long long)*step_ptr;
+  if (i < B) eps[i] = philox_normal((unsigned long long)i, 1u, seed, step);
+  if (i < (long long)B * n) noise[i] = philox_normal((unsigned long long)i, 0u, seed, step);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Sample post-processing (callbacks.py:152-154): images = clamp(x * std * 2 + mean, 0, 1) -> NHWC -> * 255 -> uint8.
 // One thread per pixel; explicit round-to-nearest multiplies / adds in torch's operation order so the truncated byte
 // is bit-identical to the reference's (no FMA contraction).
@@ -1152,6 +1256,30 @@ int diffuse(const float* clean, const float* eps, const float* noise, float P_me
             float* sigma, int B, int n, cudaStream_t stream) {
   const long long tot = (long long)B * n;
   launch_pdl(diffuse_kernel, (unsigned)((tot + 255) / 256), 256, 0, stream, clean, eps, noise, P_mean, P_std, noisy, sigma, B, n);
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+
+int diffuse_philox(const float* clean, unsigned long long seed, const long long* step_ptr, float P_mean, float P_std,
+                   float sigma_data, float* noisy, float* sigma, __nv_bfloat16* xcol, int B, int Ci, int H, int W,
+                   cudaStream_t stream) {
+  TEDM_CHECK(xcol == nullptr || 9 * (Ci + 1) <= 64, "diffuse: the fused patch gather supports at most 6 image channels (got %d)", Ci);
+  TEDM_CHECK((long long)B * H * W < (1ll << 28), "diffuse: too many pixels (%d x %d x %d)", B, H, W);
+  const long long total = (long long)B * H * W * 8;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  switch (Ci) {
+    case 1: launch_pdl(diffuse_philox_kernel<1>, grid, 256, 0, stream, clean, seed, step_ptr, P_mean, P_std, sigma_data, noisy, sigma, xcol, B, Ci, H, W); break;
+    case 3: launch_pdl(diffuse_philox_kernel<3>, grid, 256, 0, stream, clean, seed, step_ptr, P_mean, P_std, sigma_data, noisy, sigma, xcol, B, Ci, H, W); break;
+    case 4: launch_pdl(diffuse_philox_kernel<4>, grid, 256, 0, stream, clean, seed, step_ptr, P_mean, P_std, sigma_data, noisy, sigma, xcol, B, Ci, H, W); break;
+    default: launch_pdl(diffuse_philox_kernel<0>, grid, 256, 0, stream, clean, seed, step_ptr, P_mean, P_std, sigma_data, noisy, sigma, xcol, B, Ci, H, W); break;
+  }
+  TEDM_LAUNCH_CHECK();
+  return 0;
+}
+int philox_normal_draws(unsigned long long seed, const long long* step_ptr, float* eps, float* noise, int B, long long n,
+                        cudaStream_t stream) {
+  const long long tot = (long long)B * n > B ? (long long)B * n : B;
+  launch_pdl(philox_draws_kernel, (unsigned)((tot + 255) / 256), 256, 0, stream, seed, step_ptr, eps, noise, B, n);
   TEDM_LAUNCH_CHECK();
   return 0;
 }

@@ -34,12 +34,42 @@ except Exception:  # noqa: BLE001
 
 
 class Diffuser(nn.Module):
-    """ln(sigma) ~ N(P_mean, P_std); returns (clean + sigma * n, sigma) — edm.py:64-96."""
+    """ln(sigma) ~ N(P_mean, P_std); returns (clean + sigma * n, sigma) — edm.py:64-96.
+
+    Both normal draws are made inside ONE kernel (tedm_diffuse_philox, counter-based Philox4x32-10 keyed by
+    (seed, step, element)) instead of two torch Philox launches plus three elementwise launches. `seed` is taken from
+    torch's default generator at first use (so `torch.manual_seed` makes a run reproducible, as with the reference's
+    `torch.randn`), XORed with the process rank; `step` is a device counter advanced per call — inside a captured CUDA
+    graph too, so every replay draws fresh noise. When an `EDM` owns this diffuser, the same kernel also emits the
+    Denoiser's input block (c_in * noisy, ones channel, 3x3 patch gather: networks.py:578-587) and hands it over on the
+    returned tensor (`noisy._tedm_xcol`), so the image never makes a second trip through HBM before conv_in.
+    """
 
     def __init__(self, P_mean: float, P_std: float) -> None:
         super().__init__()
         self.P_mean = P_mean
         self.P_std = P_std
+        self._seed: int | None = None
+        self._step: Tensor | None = None
+        self._fuse_sigma_data: float | None = None     # set by EDM: the sigma_data of the denoiser that consumes `noisy`
+
+    def seed(self, seed: int, step: int = 0) -> None:
+        """Explicit (seed, step) of the draw stream; `step` counts the calls made so far."""
+        self._seed = int(seed)
+        if self._step is not None:
+            self._step.fill_(int(step))
+        else:
+            self._pending_step = int(step)
+
+    def _state(self, device) -> tuple[int, Tensor]:
+        if self._seed is None:
+            rank = 0
+            if torch.distributed.is_available() and torch.distributed.is_initialized():
+                rank = torch.distributed.get_rank()
+            self._seed = int(torch.randint(0, 2 ** 62, (1,)).item()) ^ (rank * 0x9E3779B97F4A7C15 & (2 ** 63 - 1))
+        if self._step is None or self._step.device != device:
+            self._step = torch.full((1,), getattr(self, "_pending_step", 0), dtype=torch.int64, device=device)
+        return self._seed, self._step
 
     @torch.no_grad()
     def forward(self, clean_image: Tensor) -> tuple[Tensor, Tensor]:
@@ -47,10 +77,20 @@ class Diffuser(nn.Module):
             raise RuntimeError("tinyedm_b200.Diffuser runs on CUDA (sm_100a) only; there is no CPU fallback")
         ops.ensure_device(clean_image.device)
         clean = ops.check(clean_image.float().contiguous(), F32, "clean_image")
-        # the two draws come from torch's Philox stream in the reference's order (epsilon first, then the noise)
-        eps = torch.randn(clean.shape[0], device=clean.device, dtype=F32)
-        noise = torch.randn_like(clean)
-        return ops.diffuse(clean, eps, noise, float(self.P_mean), float(self.P_std))
+        if clean.dim() != 4:
+            raise RuntimeError("tinyedm_b200.Diffuser expects (B, C, H, W) images")
+        seed, step = self._state(clean.device)
+        step += 1
+        sd = self._fuse_sigma_data if 9 * (clean.shape[1] + 1) <= 64 else None
+        noisy, sigma, xcol = ops.diffuse_philox(clean, seed, step, float(self.P_mean), float(self.P_std), sd)
+        if xcol is not None:
+            noisy._tedm_xcol = (xcol, float(sd), sigma.data_ptr())    # picked up by DenoiserEngine.forward
+        return noisy, sigma
+
+    def draws(self, batch: int, n: int, device) -> tuple[Tensor, Tensor]:
+        """(epsilon (B,), noise (B, n)) of the MOST RECENT call, regenerated from (seed, step): for tests and debugging."""
+        seed, step = self._state(torch.device(device))
+        return ops.philox_normal_draws(seed, step, batch, n)
 
     def extra_repr(self) -> str:
         return f"P_mean={self.P_mean}, P_std={self.P_std}"
@@ -84,6 +124,8 @@ class EDM(_Base):
         self.train_mse = WeightedMeanSquaredError()
         self.val_mse = WeightedMeanSquaredError()
         self.solver = None
+        if isinstance(diffuser, Diffuser) and hasattr(denoiser, "sigma_data"):
+            diffuser._fuse_sigma_data = float(denoiser.sigma_data)      # the input block rides in the diffuser's kernel
         if HAVE_LIGHTNING:  # pragma: no cover - the reference's checkpoints carry the deinstantiate tree (edm.py:154-157)
             self.hparams.update(self.save_config())
 
