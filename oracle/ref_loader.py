@@ -8,9 +8,9 @@ or None when the bytecode is absent or was built by another Python. `reference_e
 """
 from __future__ import annotations
 
-import importlib.machinery
-import importlib.util
+import marshal
 import os
+import sys
 import types
 import warnings
 
@@ -20,13 +20,15 @@ _cache: dict = {}
 
 
 def _load_one(name: str):
-    path = os.path.join(REF_DIR, name + ".pyc")
+    path = os.path.join(REF_DIR, name + ".code")
     if not os.path.exists(path):
         return None
-    loader = importlib.machinery.SourcelessFileLoader(f"tinyedm_ref_{name}", path)
-    spec = importlib.util.spec_from_loader(loader.name, loader)
-    mod = importlib.util.module_from_spec(spec)
-    loader.exec_module(mod)
+    with open(path, "rb") as fh:
+        code = marshal.loads(fh.read())
+    mod = types.ModuleType(f"tinyedm_ref_{name}")
+    mod.__file__ = path
+    sys.modules[mod.__name__] = mod
+    exec(code, mod.__dict__)
     return mod
 
 

@@ -128,9 +128,12 @@ def test_training_step_uses_the_fused_input_block_and_graph_replays_draw_fresh_n
         assert calls and torch.isfinite(D).all()
     finally:
         ops.conv_in_im2col = orig
+    # (an autograd graph that is still alive pins the parameters' AccumulateGrad nodes to the stream it was built on — the
+    # default stream here — and a capture on another stream would have to synchronise with it)
+    del D, e, noisy, sigma
     opt = T.FusedAdamEMA(model.parameters(), lr=1e-4)
     step = T.GraphedTrainStep(model, opt, (clean, labels), warmup=1)
-    assert step.graph is not None, step.error
+    assert step.graph is not None, getattr(step, "error_traceback", step.error)
     losses = [float(step((clean, labels))) for _ in range(4)]
     assert len({round(l, 6) for l in losses}) == 4, losses     # same batch, different sigma / noise on every replay
     assert abs(losses[0] - l1) > 0

@@ -985,8 +985,26 @@ __device__ __forceinline__ float philox_normal(unsigned long long e, uint32_t ta
   return rad * ((e & 1) ? sn : cs);
 }
 
-// one thread per (pixel, group of 8 patch columns) exactly like conv_in_im2col_kernel; the g == 0 thread of a pixel also
-// writes the pixel's `noisy` values, the first thread of an image its sigma
+// the four normals of Philox call `call` (elements 4 call .. 4 call + 3), same values as philox_normal element by element
+__device__ __forceinline__ void philox_normal4(unsigned long long call, uint32_t tag, unsigned long long seed,
+                                               unsigned long long step, float out[4]) {
+  const uint4 r = philox4x32_10((uint32_t)call, (uint32_t)(call >> 32) | (tag << 30), (uint32_t)step, (uint32_t)(step >> 32),
+                                (uint32_t)seed, (uint32_t)(seed >> 32));
+  const float u1 = ((float)(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)(r.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u3 = ((float)(r.z >> 8) + 0.5f) * (1.0f / 16777216.0f), u4 = ((float)(r.w >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float ra = sqrtf(-2.0f * logf(u1)), rb = sqrtf(-2.0f * logf(u3));
+  float sn, cs;
+  sincospif(2.0f * u2, &sn, &cs);
+  out[0] = ra * cs; out[1] = ra * sn;
+  sincospif(2.0f * u4, &sn, &cs);
+  out[2] = rb * cs; out[3] = rb * sn;
+}
+
+// One CTA per (image, block of kDiffRows rows). Phase 1 draws the noise of those rows plus a one-row halo above and
+// below (every Philox call yields four consecutive pixels of a row; the halo rows are drawn again by the neighbouring
+// CTA — the value of an element depends on its index only), writes `noisy` for its own rows and parks c_in * noisy for
+// all of them in a zero-bordered shared-memory tile. Phase 2 is conv_in_im2col_kernel's gather out of that tile.
+constexpr int kDiffRows = 8;
 template <int CI>
 __global__ void __launch_bounds__(256)
 diffuse_philox_kernel(const float* __restrict__ clean, unsigned long long seed, const long long* __restrict__ step_ptr,
@@ -994,50 +1012,86 @@ diffuse_philox_kernel(const float* __restrict__ clean, unsigned long long seed, 
                       __nv_bfloat16* __restrict__ xcol, int B, int Ci_rt, int H, int W) {
   pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
   pdl_wait();      // ... and this one was: everything below needs its predecessors complete
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (pixel, group of 8 k)
-  const long long total = (long long)B * H * W * 8;
-  if (idx >= total) return;
-  const unsigned long long step = (unsigned long long)*step_ptr;
+  extern __shared__ float tile[];      // [Ci][kDiffRows + 2][W + 2], border = 0 (the conv's zero padding)
   const int Ci = CI > 0 ? CI : Ci_rt;
-  const int g = (int)(idx & 7);
-  const int pix = (int)(idx >> 3);
-  const int hw = H * W;
-  const int b = pix / hw, p = pix - b * hw;
-  const int h = p / W, w = p - h * W;
+  const int row_blocks = (H + kDiffRows - 1) / kDiffRows;
+  const int b = blockIdx.x / row_blocks;
+  const int h0 = (blockIdx.x - b * row_blocks) * kDiffRows;
+  const unsigned long long step = (unsigned long long)*step_ptr;
+  const int hw = H * W, TW = W + 2, TR = kDiffRows + 2;
   const float s = __expf(P_mean + philox_normal((unsigned long long)b, 1u, seed, step) * P_std);
-  const size_t img = (size_t)b * Ci * hw;
-  if (g == 0) {
-    if (p == 0) sigma[b] = s;
-    for (int ci = 0; ci < Ci; ++ci) {
-      const size_t e = img + (size_t)ci * hw + p;
-      noisy[e] = clean[e] + philox_normal(e, 0u, seed, step) * s;
-    }
-  }
-  if (xcol == nullptr) return;
+  if (h0 == 0 && threadIdx.x == 0) sigma[b] = s;
   const float c_in = rsqrtf(sigma_data * sigma_data + s * s);
-  const int cin = Ci + 1;
-  float v[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int k = g * 8 + i;
-    float val = 0.f;
-    if (k < 9 * cin) {
-      const int tap = k / cin, ci = k - tap * cin;
-      const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-      if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
-        if (ci < Ci) {
-          const size_t e = img + (size_t)(ci * H + hh) * W + ww;
-          val = c_in * (clean[e] + philox_normal(e, 0u, seed, step) * s);   // the same fp32 value the owner of e stores
-        } else {
-          val = 1.0f;
-        }
+  const bool want_tile = xcol != nullptr;
+  if (want_tile)
+    for (int i = threadIdx.x; i < Ci * TR * TW; i += blockDim.x) tile[i] = 0.f;
+  __syncthreads();
+  const size_t img = (size_t)b * Ci * hw;
+  const int r_lo = want_tile ? -1 : 0, r_hi = want_tile ? kDiffRows + 1 : kDiffRows;
+  if ((W & 3) == 0) {
+    const int W4 = W >> 2;
+    const int n_items = Ci * (r_hi - r_lo) * W4;
+    for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
+      const int w4 = i % W4;
+      const int t = i / W4;
+      const int r = t % (r_hi - r_lo) + r_lo, ci = t / (r_hi - r_lo);
+      const int hh = h0 + r;
+      if (hh < 0 || hh >= H) continue;
+      const size_t e = img + (size_t)(ci * H + hh) * W + w4 * 4;       // multiple of 4: one Philox call
+      float n4[4];
+      philox_normal4(e >> 2, 0u, seed, step, n4);
+      const float4 c = *reinterpret_cast<const float4*>(clean + e);
+      const float4 v = make_float4(c.x + n4[0] * s, c.y + n4[1] * s, c.z + n4[2] * s, c.w + n4[3] * s);
+      if (r >= 0 && r < kDiffRows) *reinterpret_cast<float4*>(noisy + e) = v;
+      if (want_tile) {
+        float* t_row = tile + (ci * TR + r + 1) * TW + 1 + w4 * 4;
+        t_row[0] = c_in * v.x; t_row[1] = c_in * v.y; t_row[2] = c_in * v.z; t_row[3] = c_in * v.w;
       }
     }
-    v[i] = val;
+  } else {
+    const int n_items = Ci * (r_hi - r_lo) * W;
+    for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
+      const int ww = i % W;
+      const int t = i / W;
+      const int r = t % (r_hi - r_lo) + r_lo, ci = t / (r_hi - r_lo);
+      const int hh = h0 + r;
+      if (hh < 0 || hh >= H) continue;
+      const size_t e = img + (size_t)(ci * H + hh) * W + ww;
+      const float v = clean[e] + philox_normal(e, 0u, seed, step) * s;
+      if (r >= 0 && r < kDiffRows) noisy[e] = v;
+      if (want_tile) tile[(ci * TR + r + 1) * TW + 1 + ww] = c_in * v;
+    }
   }
-  uint4 o;
-  o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-  *reinterpret_cast<uint4*>(xcol + (size_t)pix * 64 + g * 8) = o;
+  if (!want_tile) return;
+  __syncthreads();
+  const int cin = Ci + 1;
+  const int rows_here = min(kDiffRows, H - h0);
+  for (int i = threadIdx.x; i < rows_here * W * 8; i += blockDim.x) {
+    const int g = i & 7;
+    const int pl = i >> 3;
+    const int r = pl / W, w = pl - r * W;
+    const int h = h0 + r;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      float val = 0.f;
+      if (k < 9 * cin) {
+        const int tap = k / cin, ci = k - tap * cin;
+        const int dr = tap / 3, dc = tap % 3;              // tile coordinates already include the +1 border shift
+        if (ci < Ci) {
+          val = tile[(ci * TR + r + dr) * TW + w + dc];
+        } else {
+          const int hh = h + dr - 1, ww = w + dc - 1;
+          val = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? 1.0f : 0.f;
+        }
+      }
+      v[j] = val;
+    }
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(xcol + ((size_t)b * hw + (size_t)h * W + w) * 64 + g * 8) = o;
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -1265,13 +1319,15 @@ int diffuse_philox(const float* clean, unsigned long long seed, const long long*
                    cudaStream_t stream) {
   TEDM_CHECK(xcol == nullptr || 9 * (Ci + 1) <= 64, "diffuse: the fused patch gather supports at most 6 image channels (got %d)", Ci);
   TEDM_CHECK((long long)B * H * W < (1ll << 28), "diffuse: too many pixels (%d x %d x %d)", B, H, W);
-  const long long total = (long long)B * H * W * 8;
-  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (B <= 0) return 0;
+  const size_t smem = xcol != nullptr ? (size_t)Ci * (kDiffRows + 2) * (W + 2) * sizeof(float) : 0;
+  TEDM_CHECK(smem <= 48 * 1024, "diffuse: image rows of %d pixels x %d channels do not fit the staging tile", W, Ci);
+  const unsigned grid = (unsigned)(B * ((H + kDiffRows - 1) / kDiffRows));
   switch (Ci) {
-    case 1: launch_pdl(diffuse_philox_kernel<1>, grid, 256, 0, stream, clean, seed, step_ptr, P_mean, P_std, sigma_data, noisy, sigma, xcol, B, Ci, H, W); break;
-    case 3: launch_pdl(diffuse_philox_kernel<3>, grid, 256, 0, stream, clean, seed, step_ptr, P_mean, P_std, sigma_data, noisy, sigma, xcol, B, Ci, H, W); break;
-    case 4: launch_pdl(diffuse_philox_kernel<4>, grid, 256, 0, stream, clean, seed, step_ptr, P_mean, P_std, sigma_data, noisy, sigma, xcol, B, Ci, H, W); break;
-    default: launch_pdl(diffuse_philox_kernel<0>, grid, 256, 0, stream, clean, seed, step_ptr, P_mean, P_std, sigma_data, noisy, sigma, xcol, B, Ci, H, W); break;
+    case 1: launch_pdl(diffuse_philox_kernel<1>, grid, 256, smem, stream, clean, seed, step_ptr, P_mean, P_std, sigma_data, noisy, sigma, xcol, B, Ci, H, W); break;
+    case 3: launch_pdl(diffuse_philox_kernel<3>, grid, 256, smem, stream, clean, seed, step_ptr, P_mean, P_std, sigma_data, noisy, sigma, xcol, B, Ci, H, W); break;
+    case 4: launch_pdl(diffuse_philox_kernel<4>, grid, 256, smem, stream, clean, seed, step_ptr, P_mean, P_std, sigma_data, noisy, sigma, xcol, B, Ci, H, W); break;
+    default: launch_pdl(diffuse_philox_kernel<0>, grid, 256, smem, stream, clean, seed, step_ptr, P_mean, P_std, sigma_data, noisy, sigma, xcol, B, Ci, H, W); break;
   }
   TEDM_LAUNCH_CHECK();
   return 0;

@@ -61,8 +61,10 @@ class GraphedTrainStep:
             try:
                 self._capture()
             except Exception as e:  # noqa: BLE001 - any capture failure degrades to the eager step
+                import traceback
                 self.graph = None
                 self.error = f"{type(e).__name__}: {e}"
+                self.error_traceback = traceback.format_exc()
                 torch.cuda.synchronize()
 
     def _fwd_bwd(self) -> Tensor:
