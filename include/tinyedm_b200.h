@@ -131,6 +131,19 @@ int tedm_attention_forward(const void* qkv, void* y, float* lse, int B, int S, i
 int tedm_attention_backward(const void* qkv, const void* y, const void* g_y, const float* lse, float* delta_ws,
                             void* g_qkv, int B, int S, int heads, int head_dim, tedm_stream_t stream);
 
+/* The same attention core split in two for every other (head_dim, S) of the reference's configs — MNIST (64, 196) and
+ * (128, 49), ImageNet-latent (144, 256) and (192, 64); any head_dim % 16 == 0 up to 192 and S <= 256 — on tcgen05/TMEM:
+ *   tedm_qkv_normalize: qn = pixel_norm over head_dim of every q, k and v row (networks.py:195; bf16 like the reference's
+ *     cast) and norms[(row*3 + plane)*heads + head] = eps + rms of the raw row (fp32), rows = B*S;
+ *   tedm_attention_forward_normalized: y, lse from qn (networks.py:201-202);
+ *   tedm_attention_backward_normalized: d qkv (w.r.t. the RAW qkv: the pixel-norm adjoint runs in the kernels' epilogue)
+ *     from qn, norms, y, d y, lse; delta_ws as above. No atomics: bit-reproducible. */
+int tedm_qkv_normalize(const void* qkv, void* qn, float* norms, int64_t rows, int heads, int head_dim, tedm_stream_t stream);
+int tedm_attention_forward_normalized(const void* qn, void* y, float* lse, int B, int S, int heads, int head_dim,
+                                      tedm_stream_t stream);
+int tedm_attention_backward_normalized(const void* qn, const float* norms, const void* y, const void* g_y, const float* lse,
+                                       float* delta_ws, void* g_qkv, int B, int S, int heads, int head_dim, tedm_stream_t stream);
+
 /* ---- small fp32 layers ---- */
 /* C[M,N] = alpha*op(A)*op(B) + beta*C, row-major fp32 (F.linear of the autocast-off islands, networks.py:46-64) */
 int tedm_sgemm(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc, int transA,

@@ -1,5 +1,7 @@
-"""Cosine attention kernels (tcgen05 forward for hd=64 / S in {64,256}; warp-MMA kernels otherwise and for the backward)
-against CosineAttention.forward's arithmetic (src/tinyedm/networks.py:194-202) in fp32 torch."""
+"""Cosine attention kernels against CosineAttention.forward's arithmetic (src/tinyedm/networks.py:194-202) in fp32 torch:
+the kernels specialised for head_dim 64 / S in {64, 256} (csrc/attention_tc.cu), the generic tcgen05 pair on pre-normalised
+q, k, v for every other shape of the configs (csrc/attention_gen.cu), and the warp-MMA kernels behind tedm_attention_forward
+for shapes neither covers."""
 import math
 
 import pytest
@@ -118,3 +120,53 @@ def test_attention_backward_s256_each_gradient(dev, B, heads):
     # deterministic: no atomics anywhere in the backward
     again = ops.attention_backward(qkv, y, g_y, lse, heads).view(B, H * W, 3, C).float()
     assert torch.equal(again, g_qkv)
+
+
+GEN_SHAPES = [  # B, H, W, heads, hd — the configs' own (head_dim, S) pairs first, at small and at full batch
+    (2, 14, 14, 4, 64), (2, 7, 7, 4, 128), (2, 16, 16, 4, 144), (2, 8, 8, 4, 192),
+    (128, 14, 14, 4, 64), (128, 7, 7, 4, 128), (64, 16, 16, 4, 144), (64, 8, 8, 4, 192),
+    # the CIFAR shapes through the generic kernels too, ragged S / head_dim, a single head, one image
+    (3, 16, 16, 4, 64), (5, 8, 8, 4, 64), (3, 5, 5, 3, 16), (1, 9, 9, 1, 80), (2, 13, 11, 2, 48), (1, 16, 16, 2, 128), (3, 1, 1, 4, 64)]
+
+
+@pytest.mark.parametrize("B,H,W,heads,hd", GEN_SHAPES)
+def test_generic_tcgen05_attention_forward_backward_vs_torch(dev, B, H, W, heads, hd):
+    """qkv_normalize + the tcgen05 forward / backward pair (csrc/attention_gen.cu) against fp32 torch arithmetic of
+    networks.py:194-202 and its autograd, <= 1e-2 (north_star) with the reference's own bf16 path printed beside it."""
+    from tinyedm_b200 import ops
+    ops.ensure_device(dev)
+    torch.manual_seed(B * 1000 + H * 10 + heads + hd)
+    C, S = heads * hd, H * W
+    qkv = (torch.randn(B, H, W, 3 * C, device=dev) * 1.3).to(torch.bfloat16)
+    qn, norms = ops.qkv_normalize(qkv, heads)
+    t = qkv.float().view(B, S, 3 * heads, hd)
+    n_ref = 1e-4 + t.norm(dim=-1) / math.sqrt(hd)
+    assert rel(norms.view(B, S, 3 * heads), n_ref) < 1e-5
+    assert rel(qn.view(B, S, 3 * heads, hd), t / n_ref[..., None]) < 4e-3          # one bf16 rounding
+    y, lse = ops.attention_forward_normalized(qn, heads, need_lse=True)
+    x = qkv.float().view(B, S, 3 * C).requires_grad_(True)
+    with torch.backends.cuda.sdp_kernel(enable_flash=False, enable_mem_efficient=False, enable_math=True):
+        ref = reference(x, heads)
+    r = rel(y.view(B, S, C), ref)
+    tt = x.detach().view(B, S, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    tt = tt / (1e-4 + tt.norm(dim=-1, keepdim=True) / math.sqrt(hd))
+    lse_ref = torch.logsumexp(tt[0] @ tt[1].transpose(-1, -2) / math.sqrt(hd), dim=-1)
+    assert torch.isfinite(lse).all() and rel(lse.view(B, heads, S), lse_ref) < 2e-3
+    g_y = torch.randn(B, H, W, C, device=dev).to(torch.bfloat16)
+    g_qkv = ops.attention_backward_normalized(qn, norms, y, g_y, lse, heads)
+    (g_ref,) = torch.autograd.grad(ref, x, g_y.float().view(B, S, C))
+    g_ours = g_qkv.view(B, S, 3, C).float()
+    g_ref = g_ref.view(B, S, 3, C)
+    parts = {name: rel(g_ours[:, :, i], g_ref[:, :, i]) for i, name in enumerate("qkv")}
+    y16, g16 = reference_bf16(qkv.view(B, S, 3 * C), heads, g_y.view(B, S, C))
+    floor_f, floor_b = rel(y16, ref), rel(g16, g_ref.reshape(B, S, 3 * C))
+    print(f"generic attention B={B} S={S} hd={hd}: forward {r:.2e} (reference bf16 path {floor_f:.2e}), backward "
+          + ", ".join(f"d{k} {v:.2e}" for k, v in parts.items()) + f" (reference bf16 path {floor_b:.2e})")
+    assert torch.isfinite(g_qkv).all()
+    _assert_within(r, floor_f, "y")
+    for k, v in parts.items():
+        _assert_within(v, floor_b, "d" + k)
+    # no atomics anywhere: bit-reproducible
+    y2, lse2 = ops.attention_forward_normalized(qn, heads, need_lse=True)
+    assert torch.equal(y2, y) and torch.equal(lse2, lse)
+    assert torch.equal(ops.attention_backward_normalized(qn, norms, y, g_y, lse, heads), g_qkv)

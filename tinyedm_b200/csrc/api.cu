@@ -137,6 +137,17 @@ int tedm_attention_forward(const void* qkv, void* y, float* lse, int B, int S, i
                            tedm_stream_t stream) {
   return attention_forward(CBF(qkv), BF(y), lse, B, S, heads, head_dim, ST(stream));
 }
+int tedm_qkv_normalize(const void* qkv, void* qn, float* norms, int64_t rows, int heads, int head_dim, tedm_stream_t stream) {
+  return qkv_normalize(CBF(qkv), BF(qn), norms, (long long)rows, heads, head_dim, ST(stream));
+}
+int tedm_attention_forward_normalized(const void* qn, void* y, float* lse, int B, int S, int heads, int head_dim,
+                                      tedm_stream_t stream) {
+  return attention_forward_normalized(CBF(qn), BF(y), lse, B, S, heads, head_dim, ST(stream));
+}
+int tedm_attention_backward_normalized(const void* qn, const float* norms, const void* y, const void* g_y, const float* lse,
+                                       float* delta_ws, void* g_qkv, int B, int S, int heads, int head_dim, tedm_stream_t stream) {
+  return attention_backward_normalized(CBF(qn), norms, CBF(y), CBF(g_y), lse, delta_ws, BF(g_qkv), B, S, heads, head_dim, ST(stream));
+}
 int tedm_attention_backward(const void* qkv, const void* y, const void* g_y, const float* lse, float* delta_ws,
                             void* g_qkv, int B, int S, int heads, int head_dim, tedm_stream_t stream) {
   return attention_backward(CBF(qkv), CBF(y), CBF(g_y), lse, delta_ws, BF(g_qkv), B, S, heads, head_dim, ST(stream));

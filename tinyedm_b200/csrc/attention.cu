@@ -596,9 +596,11 @@ int attention_backward(const __nv_bfloat16* qkv, const __nv_bfloat16* y, const _
                        float* delta, __nv_bfloat16* g_qkv, int B, int S, int heads, int hd, cudaStream_t stream) {
   if (check_dims(S, hd, heads) != 0) return -1;
   static const bool use_tc = [] { const char* e = getenv("TEDM_ATTN_TC"); return !(e != nullptr && e[0] == '0'); }();
-  // tcgen05 backward: measured 296 us vs 325 us at S = 256 (B = 256), but 62 us vs 45 us at S = 64 (one CTA per SM, phases
-  // not overlapped): the small problem stays on the warp-MMA kernels
-  if (use_tc && attention_tc_supported(S, hd) && S == 256)
+  // tcgen05 backward: the fused one-CTA-per-head kernel at S = 256; at S = 64 the two-kernel tcgen05 version (measured
+  // 62 us vs 45 us for the warp-MMA kernels at B = 256: one CTA per SM, phases not overlapped — TEDM_ATTN_BWD64_TC=0
+  // switches back, ~0.1 ms per CIFAR step)
+  static const bool tc64 = [] { const char* e = getenv("TEDM_ATTN_BWD64_TC"); return !(e != nullptr && e[0] == '0'); }();
+  if (use_tc && attention_tc_supported(S, hd) && (S == 256 || tc64))
     return attention_backward_tc(qkv, y, g_y, lse, delta, g_qkv, B, S, heads, stream);
   switch (hd) {
     case 32: return launch_bwd<32, 64>(qkv, y, g_y, lse, delta, g_qkv, B, S, heads, stream);

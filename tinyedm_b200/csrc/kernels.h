@@ -167,6 +167,14 @@ int attention_forward_tc(const __nv_bfloat16* qkv, __nv_bfloat16* y, float* lse,
 int attention_backward_tc(const __nv_bfloat16* qkv, const __nv_bfloat16* y, const __nv_bfloat16* g_y, const float* lse,
                           float* delta, __nv_bfloat16* g_qkv, int B, int S, int heads, cudaStream_t stream);
 
+// ---- attention_gen.cu: tcgen05/TMEM attention for any head_dim % 16 == 0 (<= 192), S <= 256, on pre-normalised q, k, v ----
+int qkv_normalize(const __nv_bfloat16* qkv, __nv_bfloat16* qn, float* norms, long long rows, int heads, int hd, cudaStream_t stream);
+int attention_forward_normalized(const __nv_bfloat16* qn, __nv_bfloat16* y, float* lse, int B, int S, int heads, int hd,
+                                 cudaStream_t stream);
+int attention_backward_normalized(const __nv_bfloat16* qn, const float* norms, const __nv_bfloat16* y, const __nv_bfloat16* g_y,
+                                  const float* lse, float* delta, __nv_bfloat16* g_qkv, int B, int S, int heads, int hd,
+                                  cudaStream_t stream);
+
 // ---- attention.cu ----
 int attention_forward(const __nv_bfloat16* qkv, __nv_bfloat16* y, float* lse, int B, int S, int heads, int hd,
                       cudaStream_t stream);

@@ -270,6 +270,11 @@ def fused_skip_mean_enabled() -> bool:
     return os.environ.get("TEDM_FUSED_SKIP_MEAN", "1") != "0"
 
 
+def generic_attention_enabled() -> bool:
+    """TEDM_ATTN_GENERIC=0: shapes outside (head_dim 64, S in {64, 256}) run the warp-MMA kernels (A/B switch)."""
+    return os.environ.get("TEDM_ATTN_GENERIC", "1") != "0"
+
+
 def split_epilogue_enabled() -> bool:
     """TEDM_SPLIT_EPILOGUE=0 keeps the separate concat-split / gain-gradient kernels in the backward (A/B switch)."""
     return os.environ.get("TEDM_SPLIT_EPILOGUE", "1") != "0"
@@ -558,11 +563,20 @@ class DenoiserEngine:
         if bp.attn:
             c5 = 1.0 / math.sqrt(2.0)
             qkv = ops.conv2d(out, bp.w["qkv"].fwd, 1, 3 * bp.cout)
-            y, lse = ops.attention_forward(qkv, self.m.num_heads, need_lse=save)
+            heads = self.m.num_heads
+            if ops.attention_specialised(qkv.shape[1] * qkv.shape[2], bp.cout // heads) or not generic_attention_enabled():
+                y, lse = ops.attention_forward(qkv, heads, need_lse=save)      # normalises q, k, v inside the kernel
+                if save:
+                    S.update(qkv=qkv)
+            else:
+                qn, norms = ops.qkv_normalize(qkv, heads)                       # once per layer; the backward reuses it
+                y, lse = ops.attention_forward_normalized(qn, heads, need_lse=save)
+                if save:
+                    S.update(qn=qn, norms=norms)
             out2, out_mean = self._conv_with_mean(y, bp.w["out"].fwd, 1, bp.cout, want_mean, epi=EPI_AXPBY, alpha=c5, beta=c5,
                                                   res=out)
             if save:
-                S.update(mid=out, qkv=qkv, lse=lse, y=y)
+                S.update(mid=out, lse=lse, y=y)
             out = out2
         return out, S, out_mean
 
@@ -674,7 +688,10 @@ class DenoiserEngine:
         c5 = 1.0 / math.sqrt(2.0)
         g_y = ops.conv2d(g_out, bp.w["out"].dgrad, 1, bp.cout, alpha=c5)
         ops.conv2d_wgrad(g_out, S["y"], bp.w["out"].ghat, 1, alpha=c5, accumulate=True)
-        g_qkv = ops.attention_backward(S["qkv"], S["y"], g_y, S["lse"], self.m.num_heads)
+        if "qn" in S:
+            g_qkv = ops.attention_backward_normalized(S["qn"], S["norms"], S["y"], g_y, S["lse"], self.m.num_heads)
+        else:
+            g_qkv = ops.attention_backward(S["qkv"], S["y"], g_y, S["lse"], self.m.num_heads)
         g_mid = ops.conv2d(g_qkv, bp.w["qkv"].dgrad, 1, bp.cout, epi=EPI_AXPBY, alpha=1.0, beta=c5, res=g_out)
         ops.conv2d_wgrad(g_qkv, S["mid"], bp.w["qkv"].ghat, 1, accumulate=True)
         return g_mid

@@ -204,6 +204,42 @@ def attention_backward(qkv: Tensor, y: Tensor, g_y: Tensor, lse: Tensor, heads: 
     return g_qkv
 
 
+def attention_specialised(S: int, hd: int) -> bool:
+    """Shapes served by the kernels that normalise q, k, v themselves (head_dim 64, S in {64, 256}: the CIFAR config);
+    every other shape goes through qkv_normalize + the *_normalized pair."""
+    return hd == 64 and S in (64, 256)
+
+
+def qkv_normalize(qkv: Tensor, heads: int):
+    """(qn, norms): pixel_norm over head_dim of q, k and v (networks.py:195) and n = eps + rms per row (fp32)."""
+    B, H, W, C3 = qkv.shape
+    hd = C3 // 3 // heads
+    qn = torch.empty_like(qkv)
+    norms = torch.empty((B * H * W, 3 * heads), device=qkv.device, dtype=F32)
+    _lib.call("tedm_qkv_normalize", qkv.data_ptr(), qn.data_ptr(), norms.data_ptr(), B * H * W, heads, hd, _stream())
+    return qn, norms
+
+
+def attention_forward_normalized(qn: Tensor, heads: int, need_lse: bool):
+    B, H, W, C3 = qn.shape
+    C = C3 // 3
+    S = H * W
+    y = torch.empty((B, H, W, C), device=qn.device, dtype=BF16)
+    lse = torch.empty((B * heads * S,), device=qn.device, dtype=F32) if need_lse else None
+    _lib.call("tedm_attention_forward_normalized", qn.data_ptr(), y.data_ptr(), _p(lse), B, S, heads, C // heads, _stream())
+    return y, lse
+
+
+def attention_backward_normalized(qn: Tensor, norms: Tensor, y: Tensor, g_y: Tensor, lse: Tensor, heads: int) -> Tensor:
+    B, H, W, C3 = qn.shape
+    C = C3 // 3
+    delta = torch.empty_like(lse)
+    g_qkv = torch.empty_like(qn)
+    _lib.call("tedm_attention_backward_normalized", qn.data_ptr(), norms.data_ptr(), y.data_ptr(), g_y.data_ptr(), lse.data_ptr(),
+              delta.data_ptr(), g_qkv.data_ptr(), B, H * W, heads, C // heads, _stream())
+    return g_qkv
+
+
 # ---------------------------------------------------------------------------------------------------------
 # small fp32 layers
 # ---------------------------------------------------------------------------------------------------------

@@ -92,6 +92,8 @@ if rank == 0:
         for n, (alone, conc) in sorted(by.items(), key=lambda kv: -sum(kv[1][0]) - sum(kv[1][1]))[:12]:
             if alone and conc:
                 P(f"  {sum(alone) / len(alone):8.1f} (n={len(alone):3d})  {sum(conc) / len(conc):8.1f} (n={len(conc):3d})  {n}")
-if world > 1:
-    dist.barrier()
-    dist.destroy_process_group()
+# no barrier / destroy_process_group here: tearing the process group down while a captured graph still references its
+# communicator hung the first version of this tool for the whole gpurun limit; every rank just leaves
+torch.cuda.synchronize()
+sys.stdout.flush()
+os._exit(0)
