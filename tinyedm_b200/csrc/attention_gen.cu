@@ -45,29 +45,81 @@ __device__ __forceinline__ uint4* srow(uint8_t* slab, int r, int j) {
 // ---------------------------------------------------------------------------------------------------------------------
 // pixel_norm of the q, k, v rows (networks.py:195): one warp per (pixel, plane, head) group of hd contiguous channels
 // ---------------------------------------------------------------------------------------------------------------------
+// A group of hd channels is hd / 8 16-byte chunks (8 for hd = 64, 16 for 128, 18 for 144, 24 for 192): a warp serves
+// 32 / SEG groups at once, SEG = 8, 16 or 32 lanes per group, so that (almost) every lane has a load in flight.
+template <int SEG>
 __global__ void __launch_bounds__(256)
 qkv_norm_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ qn, float* __restrict__ norms,
                 long long n_groups, int hd) {
   pdl_trigger();
   pdl_wait();
-  const long long g = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (g >= n_groups) return;
+  constexpr int GPW = 32 / SEG;          // groups per warp
   const int lane = threadIdx.x & 31;
+  const int li = lane % SEG;
+  const long long g = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * GPW + lane / SEG;
   const int chunks = hd >> 3;            // 16-byte chunks per row (hd % 8 == 0)
+  const bool on = g < n_groups && li < chunks;
   uint4 v = make_uint4(0, 0, 0, 0);
-  if (lane < chunks) v = reinterpret_cast<const uint4*>(qkv + g * hd)[lane];
+  if (on) v = reinterpret_cast<const uint4*>(qkv + g * hd)[li];
   const float2 a = unpack_bf16(v.x), b = unpack_bf16(v.y), c = unpack_bf16(v.z), d = unpack_bf16(v.w);
   float ss = a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + c.x * c.x + c.y * c.y + d.x * d.x + d.y * d.y;
-  ss = warp_sum(ss);
+#pragma unroll
+  for (int o = SEG / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float n = kEpsG + sqrtf(ss / (float)hd);
   const float inv = 1.0f / n;
-  if (lane < chunks) {
+  if (on) {
     uint4 o;
     o.x = pack_bf16(a.x * inv, a.y * inv); o.y = pack_bf16(b.x * inv, b.y * inv);
     o.z = pack_bf16(c.x * inv, c.y * inv); o.w = pack_bf16(d.x * inv, d.y * inv);
-    reinterpret_cast<uint4*>(qn + g * hd)[lane] = o;
+    reinterpret_cast<uint4*>(qn + g * hd)[li] = o;
+    if (li == 0) norms[g] = n;
   }
-  if (lane == 0) norms[g] = n;
+}
+
+// Tile geometry. Normal mode: a tile = 128 consecutive rows (queries or keys) of ONE (image, head) pair, streamed chunk c =
+// rows 64c.. of the same pair. Packed mode (S <= 64: MNIST 7x7, ImageNet-latent 8x8, CIFAR 8x8): a tile = TWO pairs, rows
+// 0-63 the first and 64-127 the second (each padded to 64 rows), chunk c = the rows of pair c, and a row only sees the
+// columns of its own pair (block-diagonal mask) — half the CTAs and twice the useful rows per MMA.
+struct Geom {
+  int S, heads, n_pairs, pair0, t_off;
+  bool packed;
+  __device__ __forceinline__ int pair_clamped(int p) const { return p < n_pairs ? p : n_pairs - 1; }
+  // (pair, row inside the pair, valid) of tile row m
+  __device__ __forceinline__ int row_pair(int m) const { return packed ? pair_clamped(pair0 + (m >> 6)) : pair0; }
+  __device__ __forceinline__ int row_idx(int m) const { return packed ? (m & 63) : t_off + m; }
+  __device__ __forceinline__ bool row_live(int m) const {
+    return packed ? (pair0 + (m >> 6) < n_pairs && (m & 63) < S) : (t_off + m < S);
+  }
+  // is column j of chunk c a real key/query for tile row m
+  __device__ __forceinline__ bool col_live(int m, int c, int j) const {
+    return packed ? (c == (m >> 6) && j < S) : (c * 64 + j < S);
+  }
+  // pair and first tensor row of 64-row box `hh` of the resident tile / of streamed chunk c
+  __device__ __forceinline__ int box_pair(int hh) const { return packed ? pair_clamped(pair0 + hh) : pair0; }
+  __device__ __forceinline__ int res_row(int hh) const {
+    const int p = box_pair(hh);
+    return (p / heads) * S + (packed ? 0 : t_off + 64 * hh);
+  }
+  __device__ __forceinline__ int chunk_row(int c) const {
+    const int p = box_pair(c);
+    return (p / heads) * S + (packed ? 0 : 64 * c);
+  }
+  __device__ __forceinline__ int box_head(int hh) const { const int p = box_pair(hh); return p - (p / heads) * heads; }
+};
+
+__device__ __forceinline__ Geom make_geom(int S, int heads, int n_pairs) {
+  Geom g;
+  g.S = S; g.heads = heads; g.n_pairs = n_pairs;
+  g.packed = S <= 64;
+  if (g.packed) {
+    g.pair0 = blockIdx.x * 2;
+    g.t_off = 0;
+  } else {
+    const int tiles = (S + 127) >> 7;
+    g.pair0 = blockIdx.x / tiles;
+    g.t_off = (blockIdx.x - g.pair0 * tiles) * 128;
+  }
+  return g;
 }
 
 // number of 16-wide k steps / valid columns of slab s for head dim hd
@@ -92,7 +144,7 @@ struct FwdLayout {
 template <int NSLAB>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_gen_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ y, float* __restrict__ lse,
-                    int S, int hd, int heads, float scale) {
+                    int S, int hd, int heads, int n_pairs, float scale) {
   using L = FwdLayout<NSLAB>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBars);
@@ -108,12 +160,8 @@ attn_fwd_gen_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16*
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   if (threadIdx.x == 0) pdl_trigger();
   const int C = heads * hd;
-  const int q_tiles = (S + 127) >> 7;
-  const int pair = blockIdx.x / q_tiles;
-  const int q_off = (blockIdx.x - pair * q_tiles) * 128;
-  const int b = pair / heads, head = pair - b * heads;
-  const int NC = (S + 63) >> 6;           // 64-key chunks
-  const int row0 = b * S;
+  const Geom geo = make_geom(S, heads, n_pairs);
+  const int NC = geo.packed ? 2 : (S + 63) >> 6;           // 64-key chunks
 
   if (warp == 4) {
     if (lane == 0) {
@@ -142,15 +190,15 @@ attn_fwd_gen_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16*
       mbar_expect_tx(bar_q, NSLAB * kSlab128);
       for (int s = 0; s < NSLAB; ++s)
         for (int hh = 0; hh < 2; ++hh)
-          tma_load_2d(smem + L::kOffQ + s * kSlab128 + hh * kSlab64, &tmap_qkv, bar_q, head * hd + 64 * s, row0 + q_off + 64 * hh);
+          tma_load_2d(smem + L::kOffQ + s * kSlab128 + hh * kSlab64, &tmap_qkv, bar_q, geo.box_head(hh) * hd + 64 * s, geo.res_row(hh));
       for (int i = 0; i < 2 * NC; ++i) {
         const int st = i % kFwdStages;
         if (i >= kFwdStages) mbar_wait_bounded(&empty[st], ((i / kFwdStages) - 1) & 1);
         const int plane = i < NC ? 1 : 2, c = i < NC ? i : i - NC;
         mbar_expect_tx(&full[st], L::kStageBytes);
         for (int s = 0; s < NSLAB; ++s)
-          tma_load_2d(smem + L::kOffRing + st * L::kStageBytes + s * kSlab64, &tmap_qkv, &full[st], plane * C + head * hd + 64 * s,
-                      row0 + 64 * c);
+          tma_load_2d(smem + L::kOffRing + st * L::kStageBytes + s * kSlab64, &tmap_qkv, &full[st],
+                      plane * C + geo.box_head(c) * hd + 64 * s, geo.chunk_row(c));
       }
     }
   } else if (warp == 5) {
@@ -208,7 +256,7 @@ attn_fwd_gen_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16*
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        if (c0 + i < S) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(r[i]));
+        if (geo.col_live(m, c0 >> 6, (c0 & 63) + i)) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(r[i]));
     }
     const float mxs = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sc;
     float sum4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -225,7 +273,7 @@ attn_fwd_gen_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16*
         float pv[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          pv[i] = (c * 64 + h * 32 + i < S) ? exp2f(fmaf(__uint_as_float(r[i]), sc, -mxs)) : 0.f;
+          pv[i] = geo.col_live(m, c, h * 32 + i) ? exp2f(fmaf(__uint_as_float(r[i]), sc, -mxs)) : 0.f;
           sum4[i & 3] += pv[i];
         }
 #pragma unroll
@@ -244,9 +292,11 @@ attn_fwd_gen_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16*
     tc_fence_after();
     const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
     const float inv = 1.0f / sum;
-    const int q = q_off + m;
-    const bool live = q < S;
-    __nv_bfloat16* dst = y + ((long long)(row0 + (live ? q : 0))) * C + head * hd;
+    const bool live = geo.row_live(m);
+    const int pair = geo.row_pair(m);
+    const int q = live ? geo.row_idx(m) : 0;
+    const int b = pair / heads, head = pair - b * heads;
+    __nv_bfloat16* dst = y + ((long long)(b * S + q)) * C + head * hd;
     const uint32_t t_o = tmem_o + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int col = 0; col < hd; col += 32) {
@@ -366,7 +416,8 @@ template <int NSLAB, int MODE>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_gen_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ norms, const float* __restrict__ lse,
-                    float* __restrict__ delta, __nv_bfloat16* __restrict__ g_qkv, int S, int hd, int heads, float scale) {
+                    float* __restrict__ delta, __nv_bfloat16* __restrict__ g_qkv, int S, int hd, int heads, int n_pairs,
+                    float scale) {
   using L = BwdLayout<NSLAB, MODE>;
   constexpr int NB = L::kNB;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -386,12 +437,8 @@ attn_bwd_gen_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   if (threadIdx.x == 0) pdl_trigger();
   const int C = heads * hd;
-  const int tiles = (S + 127) >> 7;
-  const int pair = blockIdx.x / tiles;
-  const int t_off = (blockIdx.x - pair * tiles) * 128;      // first query (MODE 0) / key (MODE 1) row of the tile
-  const int b = pair / heads, head = pair - b * heads;
-  const int NC = (S + 63) >> 6;
-  const int row0 = b * S;
+  const Geom geo = make_geom(S, heads, n_pairs);            // tile rows: queries (MODE 0) / keys (MODE 1)
+  const int NC = geo.packed ? 2 : (S + 63) >> 6;
 
   if (warp == 8) {
     if (lane == 0) {
@@ -423,7 +470,8 @@ attn_bwd_gen_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       mbar_expect_tx(bar_res, 2 * NSLAB * kSlab128);
       for (int s = 0; s < NSLAB; ++s)
         for (int hh = 0; hh < 2; ++hh) {
-          const int r = row0 + t_off + 64 * hh;
+          const int r = geo.res_row(hh);
+          const int head = geo.box_head(hh);
           if (MODE == 0) {
             tma_load_2d(smem + L::kOffA + s * kSlab128 + hh * kSlab64, &tmap_qkv, bar_res, head * hd + 64 * s, r);
             tma_load_2d(smem + L::kOffB + s * kSlab128 + hh * kSlab64, &tmap_do, bar_res, head * hd + 64 * s, r);
@@ -438,13 +486,14 @@ attn_bwd_gen_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         mbar_expect_tx(&full[st], L::kStageBytes);
         uint8_t* xs = smem + L::kOffStage + st * L::kStageBytes;
         uint8_t* ys = xs + NSLAB * kSlab64;
+        const int head = geo.box_head(c), crow = geo.chunk_row(c);
         for (int s = 0; s < NSLAB; ++s) {
           if (MODE == 0) {   // X = K chunk, Y = V chunk
-            tma_load_2d(xs + s * kSlab64, &tmap_qkv, &full[st], C + head * hd + 64 * s, row0 + 64 * c);
-            tma_load_2d(ys + s * kSlab64, &tmap_qkv, &full[st], 2 * C + head * hd + 64 * s, row0 + 64 * c);
+            tma_load_2d(xs + s * kSlab64, &tmap_qkv, &full[st], C + head * hd + 64 * s, crow);
+            tma_load_2d(ys + s * kSlab64, &tmap_qkv, &full[st], 2 * C + head * hd + 64 * s, crow);
           } else {           // X = Q chunk, Y = dO chunk
-            tma_load_2d(xs + s * kSlab64, &tmap_qkv, &full[st], head * hd + 64 * s, row0 + 64 * c);
-            tma_load_2d(ys + s * kSlab64, &tmap_do, &full[st], head * hd + 64 * s, row0 + 64 * c);
+            tma_load_2d(xs + s * kSlab64, &tmap_qkv, &full[st], head * hd + 64 * s, crow);
+            tma_load_2d(ys + s * kSlab64, &tmap_do, &full[st], head * hd + 64 * s, crow);
           }
         }
       }
@@ -516,9 +565,12 @@ attn_bwd_gen_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     const int quarter = warp & 3;
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float sc = scale * kLog2eG;
-    const int r_idx = t_off + m;                  // row index inside the (image, head)
-    const bool live = r_idx < S;
-    const int r_cl = live ? r_idx : S - 1;
+    const bool live = geo.row_live(m);
+    const int pair = geo.row_pair(m);
+    const int b = pair / heads, head = pair - b * heads;
+    const int row0 = b * S;
+    const int r_idx = geo.row_idx(m);             // row index inside the (image, head)
+    const int r_cl = r_idx < S ? r_idx : S - 1;
     float ls2 = 0.f, dl = 0.f;
     if (MODE == 0) {
       // delta = sum_d dO * O of this query row (O straight from global, dO from the resident tile)
@@ -536,10 +588,12 @@ attn_bwd_gen_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       dl = acc;
       if (live && half == 0) delta[(long long)pair * S + r_idx] = acc;
     } else {
-      for (int i = threadIdx.x; i < NC * 64; i += 256) {
-        const int qi = i < S ? i : S - 1;
-        lse_s[i] = lse[(long long)pair * S + qi] * kLog2eG;
-        dl_s[i] = delta[(long long)pair * S + qi];
+      for (int i = threadIdx.x; i < NC * 64; i += 256) {     // statistics of the streamed queries, chunk by chunk
+        const int cp = geo.box_pair(i >> 6);
+        const int qraw = geo.packed ? (i & 63) : i;
+        const int qi = qraw < S ? qraw : S - 1;
+        lse_s[i] = lse[(long long)cp * S + qi] * kLog2eG;
+        dl_s[i] = delta[(long long)cp * S + qi];
       }
       named_bar_sync(1, 256);
     }
@@ -557,10 +611,10 @@ attn_bwd_gen_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       float pv[32], ds[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const int col = c * 64 + half * 32 + i;          // key (MODE 0) / query (MODE 1) index of this column
+        const int col = c * 64 + half * 32 + i;          // key (MODE 0) / query (MODE 1) slot of this column
         const float l2 = MODE == 0 ? ls2 : lse_s[col];
         const float dd = MODE == 0 ? dl : dl_s[col];
-        const float p = col < S ? exp2f(fmaf(__uint_as_float(rs[i]), sc, -l2)) : 0.f;
+        const float p = geo.col_live(m, c, half * 32 + i) ? exp2f(fmaf(__uint_as_float(rs[i]), sc, -l2)) : 0.f;
         pv[i] = p;
         ds[i] = p * (__uint_as_float(rp[i]) - dd) * scale;
       }
@@ -632,8 +686,10 @@ int launch_fwd_gen(const __nv_bfloat16* qn, __nv_bfloat16* y, float* lse, int B,
   static unsigned long long configured = 0;
   if (first_use_on_device(&configured))
     TEDM_CUDA(cudaFuncSetAttribute(attn_fwd_gen_kernel<NSLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmem));
-  const int grid = B * heads * ((S + 127) / 128);
-  launch_pdl(attn_fwd_gen_kernel<NSLAB>, grid, kFwdThreads, L::kSmem, stream, t_qkv, y, lse, S, hd, heads, 1.0f / sqrtf((float)hd));
+  const int n_pairs = B * heads;
+  const int grid = S <= 64 ? (n_pairs + 1) / 2 : n_pairs * ((S + 127) / 128);
+  launch_pdl(attn_fwd_gen_kernel<NSLAB>, grid, kFwdThreads, L::kSmem, stream, t_qkv, y, lse, S, hd, heads, n_pairs,
+             1.0f / sqrtf((float)hd));
   TEDM_LAUNCH_CHECK();
   return 0;
 }
@@ -648,13 +704,14 @@ int launch_bwd_gen(const __nv_bfloat16* qn, const float* norms, const __nv_bfloa
     TEDM_CUDA(cudaFuncSetAttribute(attn_bwd_gen_kernel<NSLAB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdLayout<NSLAB, 0>::kSmem));
     TEDM_CUDA(cudaFuncSetAttribute(attn_bwd_gen_kernel<NSLAB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdLayout<NSLAB, 1>::kSmem));
   }
-  const int grid = B * heads * ((S + 127) / 128);
+  const int n_pairs = B * heads;
+  const int grid = S <= 64 ? (n_pairs + 1) / 2 : n_pairs * ((S + 127) / 128);
   const float scale = 1.0f / sqrtf((float)hd);
   launch_pdl(attn_bwd_gen_kernel<NSLAB, 0>, grid, kBwdThreads, BwdLayout<NSLAB, 0>::kSmem, stream, t_qkv, t_do, y, norms, lse, delta,
-             g_qkv, S, hd, heads, scale);
+             g_qkv, S, hd, heads, n_pairs, scale);
   TEDM_LAUNCH_CHECK();
   launch_pdl(attn_bwd_gen_kernel<NSLAB, 1>, grid, kBwdThreads, BwdLayout<NSLAB, 1>::kSmem, stream, t_qkv, t_do, y, norms, lse, delta,
-             g_qkv, S, hd, heads, scale);
+             g_qkv, S, hd, heads, n_pairs, scale);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
@@ -676,7 +733,10 @@ int qkv_normalize(const __nv_bfloat16* qkv, __nv_bfloat16* qn, float* norms, lon
   TEDM_CHECK(hd % 8 == 0 && hd <= 256, "qkv_normalize: head_dim %d not supported", hd);
   const long long groups = rows * 3 * heads;
   if (groups <= 0) return 0;
-  launch_pdl(qkv_norm_kernel, (unsigned)((groups + 7) / 8), 256, 0, stream, qkv, qn, norms, groups, hd);
+  const int chunks = hd / 8;
+  if (chunks <= 8) launch_pdl(qkv_norm_kernel<8>, (unsigned)((groups + 31) / 32), 256, 0, stream, qkv, qn, norms, groups, hd);
+  else if (chunks <= 16) launch_pdl(qkv_norm_kernel<16>, (unsigned)((groups + 15) / 16), 256, 0, stream, qkv, qn, norms, groups, hd);
+  else launch_pdl(qkv_norm_kernel<32>, (unsigned)((groups + 7) / 8), 256, 0, stream, qkv, qn, norms, groups, hd);
   TEDM_LAUNCH_CHECK();
   return 0;
 }
