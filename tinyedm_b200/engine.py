@@ -212,15 +212,21 @@ class WeightBank:
             self._build_table()
             self._key = None
         if training:
+            # Forced normalisation of an already normalised weight is the identity (up to fp32 rounding): when no parameter
+            # changed since the last training-mode pass — the 2nd and 3rd micro-batch of an accumulated step — the
+            # prepared operands and the in-place rewrite are already what another pass would produce
+            key = ("train", _WEIGHTS_EPOCH[0]) + tuple(s.param._version for s in self.slots)
+            if key == self._key:
+                return
             ops.weight_prep_forward(self._table, len(self.slots), self.total_groups, True)
             # the kernel rewrote every parameter in place (networks.py:32-34): let autograd / EMA code see the mutation
             torch.autograd.graph.increment_version([s.param for s in self.slots])
-            self._key = None
+            self._key = ("train", _WEIGHTS_EPOCH[0]) + tuple(s.param._version for s in self.slots)
             return
         key = (_WEIGHTS_EPOCH[0],) + tuple(s.param._version for s in self.slots)
-        if key != self._key:
+        if key != self._key and self._key != ("train",) + key:      # (operands prepared by a training pass are current too)
             ops.weight_prep_forward(self._table, len(self.slots), self.total_groups, False)
-            self._key = key
+        self._key = key
 
     def invalidate(self) -> None:
         self._key = None
