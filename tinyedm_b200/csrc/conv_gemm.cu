@@ -357,10 +357,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const float tot = warp_transpose_reduce(dm, lane);
             if (q * 32 < rows_in_tile && pw < t.p_limit && c0 + lane < n_this)
               atomicAdd(p.d_mod + (long long)(pw / HW) * p.mod_stride + t.n0 + c0 + lane, tot);
-          } else if (valid) {
+          } else {
+            // rows of several images in one warp: one masked transpose-reduce per image instead of CW atomics per row
+            const int b_lo = __reduce_min_sync(0xffffffffu, valid ? b : 0x7fffffff);
+            const int b_hi = __reduce_max_sync(0xffffffffu, valid ? b : -1);
+            for (int bb = b_lo; bb <= b_hi; ++bb) {
+              float part[CW];
 #pragma unroll
-            for (int i = 0; i < CW; ++i)
-              if (c0 + i < n_this) atomicAdd(p.d_mod + (long long)b * p.mod_stride + t.n0 + c0 + i, dm[i]);
+              for (int i = 0; i < CW; ++i) part[i] = (valid && b == bb) ? dm[i] : 0.f;
+              const float tot = warp_transpose_reduce(part, lane);
+              if (c0 + lane < n_this) atomicAdd(p.d_mod + (long long)bb * p.mod_stride + t.n0 + c0 + lane, tot);
+            }
           }
         }
         if (valid) {
