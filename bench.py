@@ -462,6 +462,14 @@ def practical_bar(cx: Ctx) -> dict:
     torch.backends.cudnn.benchmark = True
     cfg = O.CIFAR10
     gen = torch.Generator().manual_seed(42)
+    nets = ref_loader.load().networks
+    if not getattr(nets, "_tedm_lerp_shim", False):
+        # torch 2.11 refuses Tensor.lerp with mixed dtypes (fp32 `self`, bf16 `end`), which the reference's mp_add
+        # (networks.py:87-88) meets under bf16 autocast where one operand comes out of an autocast-off island; torch
+        # 2.2.1 (the reference's pin) promoted. One cast, no arithmetic changed.
+        orig_mp_add = nets.mp_add
+        nets.mp_add = lambda a, b, t=0.5: orig_mp_add(a, b.to(a.dtype), t)
+        nets._tedm_lerp_shim = True
     den, emb = ref_loader.reference_edm_parts(cfg)
     ref_loader.load_params(den, O.init_denoiser_params(cfg["denoiser"], gen, gain_out=1.0))
     ref_loader.load_params(emb, O.init_embedding_params(cfg["embedding"], gen))
