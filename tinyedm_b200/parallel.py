@@ -68,10 +68,11 @@ def plan_buckets(unit_ranges: list[tuple[int, int]], bucket_elems: int, lone_tai
 class GradReducer:
     """Averages slices of a flat buffer over the process group, asynchronously on a side stream (CUDA) or inline (CPU)."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, inline: bool = False):
         self.group = group
         self.world = dist.get_world_size(group)
         self.backend = dist.get_backend(group)
+        self.inline = inline      # CUDA: the compute stream waits for every reduction right away (no concurrent kernels)
         self._stream = None
         self._pending = []
 
@@ -92,6 +93,8 @@ class GradReducer:
             with torch.cuda.stream(self._stream):
                 w = self._avg(t)
             self._pending.append(w)
+            if self.inline:
+                self.wait(t.device)
         else:
             self._avg(t)
 
@@ -110,10 +113,19 @@ class DistributedEDM:
     reference). Usage per step:  loss = model.training_step(batch, i); loss.backward(); ddp.finish_backward(); opt.step()
     """
 
-    def __init__(self, model, group=None, bucket_mb: float = 25.0, broadcast: bool = True):
+    def __init__(self, model, group=None, bucket_mb: float | None = None, broadcast: bool = True, inline: bool | None = None):
+        """`bucket_mb` (default 25, or TEDM_DDP_BUCKET_MB): size at which a run of completed blocks is sent. `inline`
+        (default off, or TEDM_DDP_INLINE=1): the compute stream waits for each message instead of running under it —
+        NCCL's CTAs and the persistent one-CTA-per-SM conv kernels cannot share an SM, so an overlapped message delays
+        the kernels it runs beside (profiles/r2_ddp_timeline_n8.txt); inline trades that for the bare transfer time."""
+        import os
+        if bucket_mb is None:
+            bucket_mb = float(os.environ.get("TEDM_DDP_BUCKET_MB", "25"))
+        if inline is None:
+            inline = os.environ.get("TEDM_DDP_INLINE", "0") == "1"
         self.model = model
         self.group = group
-        self.reducer = GradReducer(group)
+        self.reducer = GradReducer(group, inline=inline)
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
         eng = model.denoiser.engine
         eng.grad_sync = self

@@ -27,7 +27,7 @@ torch.manual_seed(0)
 model = build_edm(CIFAR10).to(dev).train()
 with torch.no_grad():
     model.denoiser.gain_out.fill_(1.0)
-ddp = DistributedEDM(model, bucket_mb=float(os.environ.get("TEDM_BUCKET_MB", "25"))) if world > 1 else None
+ddp = DistributedEDM(model) if world > 1 else None       # TEDM_DDP_BUCKET_MB / TEDM_DDP_INLINE are read by the wrapper
 opt = model.configure_optimizers()["optimizer"]
 for g in opt.param_groups: g["lr"] = 2e-5
 x = (0.5 * torch.randn(B, 3, 32, 32, device=dev)).clamp(-1, 1)
@@ -37,13 +37,19 @@ assert step.graph is not None, step.error
 for _ in range(5): step((x, y))
 torch.cuda.synchronize()
 if world > 1: dist.barrier()
-N_STEPS = 4
+N_STEPS = 3
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
-    for _ in range(N_STEPS): step((x, y))
+    for _ in range(N_STEPS + 2): step((x, y))
     torch.cuda.synchronize()
 if rank == 0:
     evs = sorted((e.time_range.start, e.time_range.end, e.name) for e in prof.events()
                  if e.device_time_total > 0 and e.time_range.end > e.time_range.start)
+    # the ranks enter the profiled region at different moments: the first two steps absorb that skew (their collectives
+    # wait for the slowest rank) and are dropped; a step ends with the optimiser kernel
+    ends = [b for a, b, n in evs if "adam" in n]
+    if len(ends) >= N_STEPS + 2:
+        t_cut = ends[1]
+        evs = [e for e in evs if e[0] >= t_cut]
     is_nccl = lambda n: "nccl" in n.lower()
     comp = [(a, b, n) for a, b, n in evs if not is_nccl(n)]
     comm = [(a, b, n) for a, b, n in evs if is_nccl(n)]
@@ -68,7 +74,7 @@ if rank == 0:
     with open(path, "w") as f:
         P = lambda *a: (print(*a), f.write(" ".join(str(t) for t in a) + "\n"))
         P(f"# tools/profile_ddp.py, world {world}, rank 0, {N_STEPS} graph-replayed CIFAR training steps (B=256/GPU), CUPTI kernel records;"
-          f" NCCL max_ctas={os.environ.get('TEDM_NCCL_MAX_CTAS', 'default')}, bucket {os.environ.get('TEDM_BUCKET_MB', '25')} MiB")
+          f" NCCL max_ctas={os.environ.get('TEDM_NCCL_MAX_CTAS', 'default')}, bucket {os.environ.get('TEDM_DDP_BUCKET_MB', '25')} MiB, inline={os.environ.get('TEDM_DDP_INLINE', '0')}")
         P(f"per step: span {span / N_STEPS / 1e3:.3f} ms | compute kernels busy {busy_comp / N_STEPS / 1e3:.3f} ms | NCCL kernels busy "
           f"{busy_comm / N_STEPS / 1e3:.3f} ms ({len(comm) // N_STEPS} kernels) | EXPOSED communication (NCCL running, no compute kernel) "
           f"{exposed / N_STEPS:.1f} us | idle (nothing running) {idle / N_STEPS:.1f} us")
