@@ -141,8 +141,11 @@ struct FwdLayout {
   static constexpr int kSmem = kOffBars + 256;
 };
 
+// head_dim <= 64 (NSLAB == 1): O (<= 64 columns) lands in the score columns of key chunk 0, which the softmax has consumed
+// before the first P V MMA is issued, so 256 TMEM columns and 80 KB of shared memory suffice and TWO CTAs share an SM —
+// the load / softmax / epilogue phases of one overlap the MMAs of the other (these tiles are far too small to fill an SM).
 template <int NSLAB>
-__global__ void __launch_bounds__(kFwdThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, NSLAB == 1 ? 2 : 1)
 attn_fwd_gen_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ y, float* __restrict__ lse,
                     int S, int hd, int heads, int n_pairs, float scale) {
   using L = FwdLayout<NSLAB>;
@@ -174,14 +177,14 @@ attn_fwd_gen_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16*
       mbar_fence_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_ptr, 512);
+    tmem_alloc(tmem_ptr, NSLAB == 1 ? 256 : 512);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_o = tmem_base + 256;
+  const uint32_t tmem_o = NSLAB == 1 ? tmem_base : tmem_base + 256;
   pdl_wait();
 
   if (warp == 4) {
@@ -341,7 +344,7 @@ attn_fwd_gen_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16*
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, NSLAB == 1 ? 256 : 512);
   }
 }
 
@@ -353,7 +356,10 @@ constexpr int kBwdStages = 2;
 
 template <int NSLAB, int MODE>
 struct BwdLayout {
-  static constexpr int kNB = (MODE == 1 && NSLAB == 3) ? 1 : 2;     // score buffers in TMEM == ring slots in shared memory
+  // score buffers in TMEM == ring slots in shared memory. One when TMEM is short (MODE 1 with three slabs: 128 + 2 x 192
+  // columns) and for head_dim <= 64, where 256 columns and <= 100 KB per CTA let two CTAs share an SM instead
+  static constexpr int kNB = (NSLAB == 1 || (MODE == 1 && NSLAB == 3)) ? 1 : 2;
+  static constexpr int kTmemCols = NSLAB == 1 ? 256 : 512;
   static constexpr int kRings = MODE == 1 ? 2 : 1;                  // MODE 1 keeps P^T and dS^T
   static constexpr int kOffA = 0;                                   // resident tile A (MODE 0: Qn, MODE 1: Kn)
   static constexpr int kOffB = NSLAB * kSlab128;                    // resident tile B (MODE 0: dO, MODE 1: Vn)
@@ -413,7 +419,7 @@ __device__ __forceinline__ void norm_adjoint_row(uint32_t t_acc, uint8_t* res, i
 }
 
 template <int NSLAB, int MODE>
-__global__ void __launch_bounds__(kBwdThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, NSLAB == 1 ? 2 : 1)
 attn_bwd_gen_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ norms, const float* __restrict__ lse,
                     float* __restrict__ delta, __nv_bfloat16* __restrict__ g_qkv, int S, int hd, int heads, int n_pairs,
@@ -454,7 +460,7 @@ attn_bwd_gen_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       mbar_fence_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_ptr, 512);
+    tmem_alloc(tmem_ptr, L::kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -602,38 +608,42 @@ attn_bwd_gen_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
       const int buf = c % NB;
       mbar_wait_bounded(&sp_ready[buf], (c / NB) & 1);
       tc_fence_after();
-      uint32_t rs[32], rp[32];
-      tmem_ld32(t_row + buf * 128 + half * 32, rs);
-      tmem_ld32(t_row + buf * 128 + 64 + half * 32, rp);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&sp_free[buf]);
-      float pv[32], ds[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int col = c * 64 + half * 32 + i;          // key (MODE 0) / query (MODE 1) slot of this column
-        const float l2 = MODE == 0 ? ls2 : lse_s[col];
-        const float dd = MODE == 0 ? dl : dl_s[col];
-        const float p = geo.col_live(m, c, half * 32 + i) ? exp2f(fmaf(__uint_as_float(rs[i]), sc, -l2)) : 0.f;
-        pv[i] = p;
-        ds[i] = p * (__uint_as_float(rp[i]) - dd) * scale;
-      }
       if (c >= NB) mbar_wait_bounded(&ring_free[buf], ((c / NB) - 1) & 1);
       uint8_t* ring0 = smem + L::kOffRing + buf * kRingTile;
       uint8_t* ring1 = smem + L::kOffRing + (NB + buf) * kRingTile;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 o;
-        o.x = pack_bf16(ds[g * 8 + 0], ds[g * 8 + 1]); o.y = pack_bf16(ds[g * 8 + 2], ds[g * 8 + 3]);
-        o.z = pack_bf16(ds[g * 8 + 4], ds[g * 8 + 5]); o.w = pack_bf16(ds[g * 8 + 6], ds[g * 8 + 7]);
-        *srow(MODE == 0 ? ring0 : ring1, m, half * 4 + g) = o;
-        if (MODE == 1) {
-          uint4 p4;
-          p4.x = pack_bf16(pv[g * 8 + 0], pv[g * 8 + 1]); p4.y = pack_bf16(pv[g * 8 + 2], pv[g * 8 + 3]);
-          p4.z = pack_bf16(pv[g * 8 + 4], pv[g * 8 + 5]); p4.w = pack_bf16(pv[g * 8 + 6], pv[g * 8 + 7]);
-          *srow(ring0, m, half * 4 + g) = p4;
+      for (int sub = 0; sub < 2; ++sub) {           // 16 columns at a time: ~100 registers, two CTAs per SM when NSLAB == 1
+        uint32_t rs[16], rp[16];
+        tmem_ld16(t_row + buf * 128 + half * 32 + sub * 16, rs);
+        tmem_ld16(t_row + buf * 128 + 64 + half * 32 + sub * 16, rp);
+        tmem_ld_wait();
+        float pv[16], ds[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int cj = half * 32 + sub * 16 + i;         // column inside the chunk
+          const int col = c * 64 + cj;                     // key (MODE 0) / query (MODE 1) slot of this column
+          const float l2 = MODE == 0 ? ls2 : lse_s[col];
+          const float dd = MODE == 0 ? dl : dl_s[col];
+          const float p = geo.col_live(m, c, cj) ? exp2f(fmaf(__uint_as_float(rs[i]), sc, -l2)) : 0.f;
+          pv[i] = p;
+          ds[i] = p * (__uint_as_float(rp[i]) - dd) * scale;
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint4 o;
+          o.x = pack_bf16(ds[g * 8 + 0], ds[g * 8 + 1]); o.y = pack_bf16(ds[g * 8 + 2], ds[g * 8 + 3]);
+          o.z = pack_bf16(ds[g * 8 + 4], ds[g * 8 + 5]); o.w = pack_bf16(ds[g * 8 + 6], ds[g * 8 + 7]);
+          *srow(MODE == 0 ? ring0 : ring1, m, half * 4 + sub * 2 + g) = o;
+          if (MODE == 1) {
+            uint4 p4;
+            p4.x = pack_bf16(pv[g * 8 + 0], pv[g * 8 + 1]); p4.y = pack_bf16(pv[g * 8 + 2], pv[g * 8 + 3]);
+            p4.z = pack_bf16(pv[g * 8 + 4], pv[g * 8 + 5]); p4.w = pack_bf16(pv[g * 8 + 6], pv[g * 8 + 7]);
+            *srow(ring0, m, half * 4 + sub * 2 + g) = p4;
+          }
         }
       }
+      tc_fence_before();
+      mbar_arrive(&sp_free[buf]);                     // both halves of the score buffer are in registers / written out
       fence_proxy_async_smem();
       mbar_arrive(&ring_ready[buf]);
     }
@@ -659,7 +669,7 @@ attn_bwd_gen_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
   __syncthreads();
   if (warp == 8) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, L::kTmemCols);
   }
 }
 
