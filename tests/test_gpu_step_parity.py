@@ -324,3 +324,77 @@ def test_ema_swap_invalidates_cached_normalised_weights(dev):
             d_e = model(x, sigma, labels).clone()
         assert not torch.equal(d_e, d_w)
         assert torch.equal(model(x, sigma, labels), d_w)
+
+
+def test_graphed_accumulated_step_matches_eager_accumulation_and_leaves_the_optimizer_alone(dev):
+    """`GraphedTrainStep(accumulate=3)` (imagenet.yaml:7): the captured three-micro-batch step computes what the eager
+    deferred accumulation computes from the same state and noise; building it performs NO optimiser step (the
+    warm-up used to take two hidden Adam steps)."""
+    import tinyedm_b200 as T
+    model, _ = _small_edm(dev, use_uncertainty=True)
+    model.train()
+    g = torch.Generator().manual_seed(21)
+    k, mb = 3, 4
+    clean = (0.5 * torch.randn(k * mb, 3, 16, 16, generator=g)).clamp(-1, 1).to(dev)
+    labels = torch.randint(0, 5, (k * mb,), generator=g).to(dev)
+    opt = T.FusedAdamEMA(model.parameters(), lr=1e-3, ema_length=0.13)
+    model.training_step((clean[:mb], labels[:mb]), 0)          # one training forward: every weight is on its norm sphere now
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    step = T.GraphedTrainStep(model, opt, (clean, labels), accumulate=k, warmup=1)
+    assert step.graph is not None, getattr(step, "error_traceback", step.error)
+    assert opt.current_step == 0 and opt._flat is None                       # no optimiser step was taken
+    for n, p in model.named_parameters():                                    # (re-normalising normalised weights: ~1e-7)
+        assert rel(p, before[n]) < 1e-5, n
+    # eager reference from the same state and the same noise
+    model.diffuser.seed(3, 0)
+    opt.zero_grad(set_to_none=True)
+    for j in range(k):
+        with model.denoiser.accumulate_grads(j < k - 1):
+            (model.training_step((clean[j * mb:(j + 1) * mb], labels[j * mb:(j + 1) * mb]), j) / k).backward()
+    g_eager = _grads_of(model)
+    model.diffuser.seed(3, 0)
+    step.graph.replay()
+    g_graph = _grads_of(model)
+    assert set(g_eager) == set(g_graph) and len(g_graph) == len(before)
+    worst = max((rel(g_graph[n], g_eager[n]), n) for n in g_eager if float(g_eager[n].norm()) > 0)
+    print("graphed accumulated step vs eager accumulation, worst gradient difference:", worst)
+    assert worst[0] < 1e-3          # atomically reduced sums in a different order; weights re-normalised in between
+    losses = [float(step((clean, labels))) for _ in range(5)]
+    assert opt.current_step == 5 and all(l == l for l in losses)
+
+
+def test_unchanged_weights_are_not_renormalised_twice_but_updated_ones_are(dev):
+    """WeightBank.prepare: the 2nd / 3rd micro-batch of an accumulated step finds the operands of the 1st (no parameter
+    moved), an optimiser step or an EMA swap invalidates them."""
+    import tinyedm_b200 as T
+    from tinyedm_b200 import ops
+    model, _ = _small_edm(dev)
+    model.train()
+    g = torch.Generator().manual_seed(2)
+    clean = (0.5 * torch.randn(4, 3, 16, 16, generator=g)).clamp(-1, 1).to(dev)
+    labels = torch.randint(0, 5, (4,), generator=g).to(dev)
+    calls = []
+    orig = ops.weight_prep_forward
+    ops.weight_prep_forward = lambda *a, **kw: (calls.append(a[-1]), orig(*a, **kw))[1]
+    try:
+        opt = T.FusedAdamEMA(model.parameters(), lr=1e-2)
+        def fwd_bwd():
+            opt.zero_grad(set_to_none=True)
+            model.training_step((clean, labels), 0).backward()
+        fwd_bwd()
+        n1 = len(calls)
+        assert n1 >= 2                      # denoiser + embedding banks
+        w = model.denoiser.encoder_blocks[0].conv_3x3_1.weight
+        assert rel(w.detach().flatten(1).norm(dim=1), torch.full((w.shape[0],), float(w[0].numel()) ** 0.5)) < 1e-4
+        fwd_bwd()
+        assert len(calls) == n1             # nothing changed: no second pass
+        opt.step()
+        fwd_bwd()
+        assert len(calls) == 2 * n1         # the optimiser moved the weights off the sphere: re-normalised
+        assert rel(w.detach().flatten(1).norm(dim=1), torch.full((w.shape[0],), float(w[0].numel()) ** 0.5)) < 1e-4
+        model.eval()
+        with torch.no_grad():
+            model(clean, torch.ones(4, device=dev), labels)
+        assert len(calls) == 2 * n1         # eval right after a training pass: operands are current
+    finally:
+        ops.weight_prep_forward = orig
