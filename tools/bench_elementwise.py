@@ -92,3 +92,26 @@ report("[32x32] conv_out fwd + precond                        r C, r/w image", n
 D, f_raw = ops.conv_out_forward(x, w, gain_out, noisy, sigma, 0.5, True)
 g_D = torch.randn_like(D); g_w = torch.zeros(Co, C, device=dev); g_g = torch.zeros((), device=dev)
 report("[32x32] conv_out bwd                                  r C, w C, r image", 2 * n + 2 * ni, lambda: ops.conv_out_backward(g_D, f_raw, x, w, gain_out, sigma, 0.5, g_w, g_g))
+
+# round 2: the kernels added on the HBM side — q, k, v normalisation of the generic attention path, the fused Philox
+# diffuser / input block, the fused Adam + EMA step
+for (name, Bq, S, heads, hd) in [("MNIST 14x14 hd 64", 128, 196, 4, 64), ("MNIST 7x7 hd 128", 128, 49, 4, 128),
+                                 ("ImageNet-latent 16x16 hd 144", 176, 256, 4, 144), ("ImageNet-latent 8x8 hd 192", 176, 64, 4, 192)]:
+    Hs = int(S ** 0.5)
+    qkv = rb(Bq, Hs, Hs, 3 * heads * hd)
+    nb = qkv.numel() * 2
+    report(f"qkv_normalize {name:32s} r 3C, w 3C (+norms)", 2 * nb + Bq * S * 3 * heads * 4, lambda: ops.qkv_normalize(qkv, heads))
+    del qkv
+for (name, Bd, Ci, Hd) in [("CIFAR B=256 3x32x32", 256, 3, 32), ("MNIST B=128 1x28x28", 128, 1, 28), ("ImageNet-latent B=176 4x64x64", 176, 4, 64)]:
+    clean = torch.randn(Bd, Ci, Hd, Hd, device=dev)
+    step = torch.zeros(1, dtype=torch.int64, device=dev)
+    ni = clean.numel() * 4
+    report(f"diffuse_philox + input block {name:30s} r img, w img + 128 B/pixel", 2 * ni + Bd * Hd * Hd * 128,
+           lambda: ops.diffuse_philox(clean, 1234, step, -1.2, 1.2, 0.5))
+    del clean
+import tinyedm_b200 as T
+ps = [torch.nn.Parameter(torch.randn(35_600_000 // 8, device=dev)) for _ in range(8)]
+for p_ in ps: p_.grad = torch.randn_like(p_)
+opt = T.FusedAdamEMA(ps, lr=1e-3, ema_length=0.13)
+opt.step()
+report("fused Adam + EMA, 35.6 M parameters                        r p,g,m,v,e  w p,m,v,e (36 B/param)", 36 * 35_600_000, lambda: opt.step())
