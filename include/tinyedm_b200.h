@@ -208,15 +208,15 @@ int tedm_diffuse(const float* clean, const float* eps, const float* noise, float
                  float* sigma, int B, int n, tedm_stream_t stream);
 /* Diffuser.forward (edm.py:84-93) with BOTH normal draws generated in the kernel, fused with Denoiser.forward's input
  * block (networks.py:578-587) — SURVEY.md §8f row N2. Counter-based Philox4x32-10: the draw for element e is a pure
- * function of (seed, *step, e); *step is a DEVICE int64 the caller advances per call (graph replays draw fresh noise).
+ * function of (seed, step, e); state = DEVICE int64[2] = {seed, step}, the caller advances step per call (both are read
+ * on the device, so replays of a captured graph draw fresh noise and see a re-seed).
  * Writes noisy (B,Ci,H,W) fp32, sigma (B,) and, when xcol != NULL, conv_in's im2col operand of c_in*noisy with the ones
  * channel, (B,H,W,64) bf16 — bit-identical to tedm_conv_in_im2col(noisy, sigma) (Ci <= 6). */
-int tedm_diffuse_philox(const float* clean, uint64_t seed, const int64_t* step, float P_mean, float P_std, float sigma_data,
+int tedm_diffuse_philox(const float* clean, const int64_t* state, float P_mean, float P_std, float sigma_data,
                         float* noisy, float* sigma, void* xcol, int B, int Ci, int H, int W, tedm_stream_t stream);
-/* The draws alone — eps (B,), noise (B,n) — exactly as tedm_diffuse_philox generates them at (seed, *step): lets a caller
- * (or a test) reproduce edm.py:84-93 from explicit draws with tedm_diffuse. */
-int tedm_philox_normal_draws(uint64_t seed, const int64_t* step, float* eps, float* noise, int B, int64_t n,
-                             tedm_stream_t stream);
+/* The draws alone — eps (B,), noise (B,n) — exactly as tedm_diffuse_philox generates them at state = {seed, step}: lets a
+ * caller (or a test) reproduce edm.py:84-93 from explicit draws with tedm_diffuse. */
+int tedm_philox_normal_draws(const int64_t* state, float* eps, float* noise, int B, int64_t n, tedm_stream_t stream);
 
 /* ---- optimiser step ("next" row N1): fused multi-tensor Adam + power-function EMA ----
  * Replaces optim.Adam(fused=True) (edm.py:250-253) + EMAOptimizer.update (ema.py:137-140, :273) with ONE launch.

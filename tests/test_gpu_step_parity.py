@@ -76,7 +76,7 @@ def test_diffuser_module_statistics_and_freshness(dev):
     assert float(z.abs().max()) > 4.0                          # tails are there (786 432 draws)
     noisy2, sigma2 = diff(clean)
     assert not torch.equal(sigma, sigma2) and not torch.equal(noisy, noisy2)
-    diff.seed(diff._seed, 0)                                   # rewind: the same (seed, step) gives the same draws
+    diff.seed(diff.rng_state()[0], 0)                          # rewind: the same (seed, step) gives the same draws
     noisy3, sigma3 = diff(clean)
     assert torch.equal(noisy3, noisy) and torch.equal(sigma3, sigma)
 
@@ -361,6 +361,19 @@ def test_graphed_accumulated_step_matches_eager_accumulation_and_leaves_the_opti
     assert worst[0] < 1e-3          # atomically reduced sums in a different order; weights re-normalised in between
     losses = [float(step((clean, labels))) for _ in range(5)]
     assert opt.current_step == 5 and all(l == l for l in losses)
+    # the replayed graph re-normalises the weights the optimiser moved (networks.py:32-34): after a replay every filter is
+    # back on its norm sphere, and the prepared operand is the normalised CURRENT weight
+    opt.param_groups[0]["lr"] = 0.05
+    step((clean, labels))                       # a large step pushes the weights well off the sphere ...
+    w = model.denoiser.encoder_blocks[0].conv_3x3_1.weight
+    off = rel(w.detach().flatten(1).norm(dim=1), torch.full((w.shape[0],), float(w[0].numel()) ** 0.5))
+    assert off > 1e-3, off
+    step.graph.replay()                         # ... and the next step's forward pulls them back
+    torch.cuda.synchronize()
+    assert rel(w.detach().flatten(1).norm(dim=1), torch.full((w.shape[0],), float(w[0].numel()) ** 0.5)) < 2e-4
+    slot = model.denoiser.engine.blocks[0].w["conv_3x3_1"]
+    w_hat = O.effective_weight(w.detach().cpu())
+    assert rel(slot.fwd.float().view(w.shape[0], 3, 3, w.shape[1]).permute(0, 3, 1, 2), w_hat) < 3e-3
 
 
 def test_unchanged_weights_are_not_renormalised_twice_but_updated_ones_are(dev):
@@ -385,13 +398,13 @@ def test_unchanged_weights_are_not_renormalised_twice_but_updated_ones_are(dev):
         n1 = len(calls)
         assert n1 >= 2                      # denoiser + embedding banks
         w = model.denoiser.encoder_blocks[0].conv_3x3_1.weight
-        assert rel(w.detach().flatten(1).norm(dim=1), torch.full((w.shape[0],), float(w[0].numel()) ** 0.5)) < 1e-4
+        assert rel(w.detach().flatten(1).norm(dim=1), torch.full((w.shape[0],), float(w[0].numel()) ** 0.5)) < 2e-4   # sqrt(n) (1 - eps)
         fwd_bwd()
         assert len(calls) == n1             # nothing changed: no second pass
         opt.step()
         fwd_bwd()
         assert len(calls) == 2 * n1         # the optimiser moved the weights off the sphere: re-normalised
-        assert rel(w.detach().flatten(1).norm(dim=1), torch.full((w.shape[0],), float(w[0].numel()) ** 0.5)) < 1e-4
+        assert rel(w.detach().flatten(1).norm(dim=1), torch.full((w.shape[0],), float(w[0].numel()) ** 0.5)) < 2e-4
         model.eval()
         with torch.no_grad():
             model(clean, torch.ones(4, device=dev), labels)

@@ -241,14 +241,13 @@ int tedm_diffuse(const float* clean, const float* eps, const float* noise, float
   return diffuse(clean, eps, noise, P_mean, P_std, noisy, sigma, B, n, ST(stream));
 }
 
-int tedm_diffuse_philox(const float* clean, uint64_t seed, const int64_t* step, float P_mean, float P_std, float sigma_data,
+int tedm_diffuse_philox(const float* clean, const int64_t* state, float P_mean, float P_std, float sigma_data,
                         float* noisy, float* sigma, void* xcol, int B, int Ci, int H, int W, tedm_stream_t stream) {
-  return diffuse_philox(clean, seed, reinterpret_cast<const long long*>(step), P_mean, P_std, sigma_data, noisy, sigma,
+  return diffuse_philox(clean, reinterpret_cast<const long long*>(state), P_mean, P_std, sigma_data, noisy, sigma,
                         BF(xcol), B, Ci, H, W, ST(stream));
 }
-int tedm_philox_normal_draws(uint64_t seed, const int64_t* step, float* eps, float* noise, int B, int64_t n,
-                             tedm_stream_t stream) {
-  return philox_normal_draws(seed, reinterpret_cast<const long long*>(step), eps, noise, B, (long long)n, ST(stream));
+int tedm_philox_normal_draws(const int64_t* state, float* eps, float* noise, int B, int64_t n, tedm_stream_t stream) {
+  return philox_normal_draws(reinterpret_cast<const long long*>(state), eps, noise, B, (long long)n, ST(stream));
 }
 
 int tedm_adam_chunk_elems(void) { return adam_chunk_elems(); }

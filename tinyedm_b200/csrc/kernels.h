@@ -279,11 +279,10 @@ int heun_step(const float* x0, const float* x1, const float* D, const float* d_p
               const float* ts, int step, int mode, long long n, cudaStream_t stream);
 int diffuse(const float* clean, const float* eps, const float* noise, float P_mean, float P_std, float* noisy,
             float* sigma, int B, int n, cudaStream_t stream);
-int diffuse_philox(const float* clean, unsigned long long seed, const long long* step_ptr, float P_mean, float P_std,
+int diffuse_philox(const float* clean, const long long* state, float P_mean, float P_std,
                    float sigma_data, float* noisy, float* sigma, __nv_bfloat16* xcol, int B, int Ci, int H, int W,
                    cudaStream_t stream);
-int philox_normal_draws(unsigned long long seed, const long long* step_ptr, float* eps, float* noise, int B, long long n,
-                        cudaStream_t stream);
+int philox_normal_draws(const long long* state, float* eps, float* noise, int B, long long n, cudaStream_t stream);
 
 // ---- optim.cu ----
 int adam_chunk_elems();

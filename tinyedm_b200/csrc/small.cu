@@ -955,8 +955,8 @@ __global__ void diffuse_kernel(const float* __restrict__ clean, const float* __r
 // two Philox launches, three elementwise launches and an image-sized round trip per tensor. Here ONE kernel draws both
 // normals with a counter-based Philox4x32-10 (key = seed; counter = (index / 4, stream tag, step)), so the value of
 // element e is a pure function of (seed, step, e): any thread may regenerate a neighbour's noise instead of waiting for
-// it, which is what lets the patch gather ride in the same pass. `step` lives on the device (incremented by the host
-// side per call, inside a CUDA graph too), so graph replays draw fresh noise.
+// it, which is what lets the patch gather ride in the same pass. (seed, step) live on the DEVICE (`state[0..1]`; the host side
+// increments the step per call, inside a captured CUDA graph too), so graph replays draw fresh noise and a re-seed reaches them.
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int i = 0; i < 10; ++i) {
@@ -1007,7 +1007,7 @@ __device__ __forceinline__ void philox_normal4(unsigned long long call, uint32_t
 constexpr int kDiffRows = 8;
 template <int CI>
 __global__ void __launch_bounds__(256)
-diffuse_philox_kernel(const float* __restrict__ clean, unsigned long long seed, const long long* __restrict__ step_ptr,
+diffuse_philox_kernel(const float* __restrict__ clean, const long long* __restrict__ state,
                       float P_mean, float P_std, float sigma_data, float* __restrict__ noisy, float* __restrict__ sigma,
                       __nv_bfloat16* __restrict__ xcol, int B, int Ci_rt, int H, int W) {
   pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
@@ -1017,7 +1017,7 @@ diffuse_philox_kernel(const float* __restrict__ clean, unsigned long long seed, 
   const int row_blocks = (H + kDiffRows - 1) / kDiffRows;
   const int b = blockIdx.x / row_blocks;
   const int h0 = (blockIdx.x - b * row_blocks) * kDiffRows;
-  const unsigned long long step = (unsigned long long)*step_ptr;
+  const unsigned long long seed = (unsigned long long)state[0], step = (unsigned long long)state[1];
   const int hw = H * W, TW = W + 2, TR = kDiffRows + 2;
   const float s = __expf(P_mean + philox_normal((unsigned long long)b, 1u, seed, step) * P_std);
   if (h0 == 0 && threadIdx.x == 0) sigma[b] = s;
@@ -1095,12 +1095,11 @@ diffuse_philox_kernel(const float* __restrict__ clean, unsigned long long seed, 
 }
 
 __global__ void __launch_bounds__(256)
-philox_draws_kernel(unsigned long long seed, const long long* __restrict__ step_ptr, float* __restrict__ eps,
-                    float* __restrict__ noise, int B, long long n) {
+philox_draws_kernel(const long long* __restrict__ state, float* __restrict__ eps, float* __restrict__ noise, int B, long long n) {
   pdl_trigger();   // the next kernel may be scheduled during this one's tail ...
   pdl_wait();      // ... and this one was: everything below needs its predecessors complete
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned long long step = (unsigned long long)*step_ptr;
+  const unsigned long long seed = (unsigned long long)state[0], step = (unsigned long long)state[1];
   if (i < B) eps[i] = philox_normal((unsigned long long)i, 1u, seed, step);
   if (i < (long long)B * n) noise[i] = philox_normal((unsigned long long)i, 0u, seed, step);
 }
@@ -1314,7 +1313,7 @@ int diffuse(const float* clean, const float* eps, const float* noise, float P_me
   return 0;
 }
 
-int diffuse_philox(const float* clean, unsigned long long seed, const long long* step_ptr, float P_mean, float P_std,
+int diffuse_philox(const float* clean, const long long* state, float P_mean, float P_std,
                    float sigma_data, float* noisy, float* sigma, __nv_bfloat16* xcol, int B, int Ci, int H, int W,
                    cudaStream_t stream) {
   TEDM_CHECK(xcol == nullptr || 9 * (Ci + 1) <= 64, "diffuse: the fused patch gather supports at most 6 image channels (got %d)", Ci);
@@ -1324,18 +1323,17 @@ int diffuse_philox(const float* clean, unsigned long long seed, const long long*
   TEDM_CHECK(smem <= 48 * 1024, "diffuse: image rows of %d pixels x %d channels do not fit the staging tile", W, Ci);
   const unsigned grid = (unsigned)(B * ((H + kDiffRows - 1) / kDiffRows));
   switch (Ci) {
-    case 1: launch_pdl(diffuse_philox_kernel<1>, grid, 256, smem, stream, clean, seed, step_ptr, P_mean, P_std, sigma_data, noisy, sigma, xcol, B, Ci, H, W); break;
-    case 3: launch_pdl(diffuse_philox_kernel<3>, grid, 256, smem, stream, clean, seed, step_ptr, P_mean, P_std, sigma_data, noisy, sigma, xcol, B, Ci, H, W); break;
-    case 4: launch_pdl(diffuse_philox_kernel<4>, grid, 256, smem, stream, clean, seed, step_ptr, P_mean, P_std, sigma_data, noisy, sigma, xcol, B, Ci, H, W); break;
-    default: launch_pdl(diffuse_philox_kernel<0>, grid, 256, smem, stream, clean, seed, step_ptr, P_mean, P_std, sigma_data, noisy, sigma, xcol, B, Ci, H, W); break;
+    case 1: launch_pdl(diffuse_philox_kernel<1>, grid, 256, smem, stream, clean, state, P_mean, P_std, sigma_data, noisy, sigma, xcol, B, Ci, H, W); break;
+    case 3: launch_pdl(diffuse_philox_kernel<3>, grid, 256, smem, stream, clean, state, P_mean, P_std, sigma_data, noisy, sigma, xcol, B, Ci, H, W); break;
+    case 4: launch_pdl(diffuse_philox_kernel<4>, grid, 256, smem, stream, clean, state, P_mean, P_std, sigma_data, noisy, sigma, xcol, B, Ci, H, W); break;
+    default: launch_pdl(diffuse_philox_kernel<0>, grid, 256, smem, stream, clean, state, P_mean, P_std, sigma_data, noisy, sigma, xcol, B, Ci, H, W); break;
   }
   TEDM_LAUNCH_CHECK();
   return 0;
 }
-int philox_normal_draws(unsigned long long seed, const long long* step_ptr, float* eps, float* noise, int B, long long n,
-                        cudaStream_t stream) {
+int philox_normal_draws(const long long* state, float* eps, float* noise, int B, long long n, cudaStream_t stream) {
   const long long tot = (long long)B * n > B ? (long long)B * n : B;
-  launch_pdl(philox_draws_kernel, (unsigned)((tot + 255) / 256), 256, 0, stream, seed, step_ptr, eps, noise, B, n);
+  launch_pdl(philox_draws_kernel, (unsigned)((tot + 255) / 256), 256, 0, stream, state, eps, noise, B, n);
   TEDM_LAUNCH_CHECK();
   return 0;
 }

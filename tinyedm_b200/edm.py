@@ -39,8 +39,8 @@ class Diffuser(nn.Module):
     Both normal draws are made inside ONE kernel (tedm_diffuse_philox, counter-based Philox4x32-10 keyed by
     (seed, step, element)) instead of two torch Philox launches plus three elementwise launches. `seed` is taken from
     torch's default generator at first use (so `torch.manual_seed` makes a run reproducible, as with the reference's
-    `torch.randn`), XORed with the process rank; `step` is a device counter advanced per call — inside a captured CUDA
-    graph too, so every replay draws fresh noise. When an `EDM` owns this diffuser, the same kernel also emits the
+    `torch.randn`), XORed with the process rank; `step` counts the calls. Both live in a device tensor the kernel reads, so
+    inside a captured CUDA graph every replay draws fresh noise and `seed()` reaches the replays. When an `EDM` owns this diffuser, the same kernel also emits the
     Denoiser's input block (c_in * noisy, ones channel, 3x3 patch gather: networks.py:578-587) and hands it over on the
     returned tensor (`noisy._tedm_xcol`), so the image never makes a second trip through HBM before conv_in.
     """
@@ -49,27 +49,38 @@ class Diffuser(nn.Module):
         super().__init__()
         self.P_mean = P_mean
         self.P_std = P_std
-        self._seed: int | None = None
-        self._step: Tensor | None = None
+        self._rng: Tensor | None = None                # device int64 {seed, step}: read by the kernel, so graph replays follow it
+        self._pending: tuple[int, int] | None = None   # seed() before the first CUDA call
         self._fuse_sigma_data: float | None = None     # set by EDM: the sigma_data of the denoiser that consumes `noisy`
 
     def seed(self, seed: int, step: int = 0) -> None:
         """Explicit (seed, step) of the draw stream; `step` counts the calls made so far."""
-        self._seed = int(seed)
-        if self._step is not None:
-            self._step.fill_(int(step))
+        if self._rng is not None:
+            self._rng.copy_(torch.tensor([int(seed) & (2 ** 63 - 1), int(step)], dtype=torch.int64))
         else:
-            self._pending_step = int(step)
+            self._pending = (int(seed) & (2 ** 63 - 1), int(step))
 
-    def _state(self, device) -> tuple[int, Tensor]:
-        if self._seed is None:
-            rank = 0
-            if torch.distributed.is_available() and torch.distributed.is_initialized():
-                rank = torch.distributed.get_rank()
-            self._seed = int(torch.randint(0, 2 ** 62, (1,)).item()) ^ (rank * 0x9E3779B97F4A7C15 & (2 ** 63 - 1))
-        if self._step is None or self._step.device != device:
-            self._step = torch.full((1,), getattr(self, "_pending_step", 0), dtype=torch.int64, device=device)
-        return self._seed, self._step
+    def rng_state(self) -> tuple[int, int]:
+        """(seed, calls made so far)."""
+        if self._rng is None:
+            return self._pending if self._pending is not None else (0, 0)
+        s = self._rng.tolist()
+        return int(s[0]), int(s[1])
+
+    def _state(self, device) -> Tensor:
+        if self._rng is None or self._rng.device != device:
+            if self._rng is not None:
+                seed, step = self.rng_state()
+            elif self._pending is not None:
+                seed, step = self._pending
+            else:
+                rank = 0
+                if torch.distributed.is_available() and torch.distributed.is_initialized():
+                    rank = torch.distributed.get_rank()
+                seed = (int(torch.randint(0, 2 ** 62, (1,)).item()) ^ (rank * 0x9E3779B97F4A7C15)) & (2 ** 63 - 1)
+                step = 0
+            self._rng = torch.tensor([seed, step], dtype=torch.int64).to(device)
+        return self._rng
 
     @torch.no_grad()
     def forward(self, clean_image: Tensor) -> tuple[Tensor, Tensor]:
@@ -79,18 +90,17 @@ class Diffuser(nn.Module):
         clean = ops.check(clean_image.float().contiguous(), F32, "clean_image")
         if clean.dim() != 4:
             raise RuntimeError("tinyedm_b200.Diffuser expects (B, C, H, W) images")
-        seed, step = self._state(clean.device)
-        step += 1
+        state = self._state(clean.device)
+        state[1:2] += 1
         sd = self._fuse_sigma_data if 9 * (clean.shape[1] + 1) <= 64 else None
-        noisy, sigma, xcol = ops.diffuse_philox(clean, seed, step, float(self.P_mean), float(self.P_std), sd)
+        noisy, sigma, xcol = ops.diffuse_philox(clean, state, float(self.P_mean), float(self.P_std), sd)
         if xcol is not None:
             noisy._tedm_xcol = (xcol, float(sd), sigma.data_ptr())    # picked up by DenoiserEngine.forward
         return noisy, sigma
 
     def draws(self, batch: int, n: int, device) -> tuple[Tensor, Tensor]:
         """(epsilon (B,), noise (B, n)) of the MOST RECENT call, regenerated from (seed, step): for tests and debugging."""
-        seed, step = self._state(torch.device(device))
-        return ops.philox_normal_draws(seed, step, batch, n)
+        return ops.philox_normal_draws(self._state(torch.device(device)), batch, n)
 
     def extra_repr(self) -> str:
         return f"P_mean={self.P_mean}, P_std={self.P_std}"

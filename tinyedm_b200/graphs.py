@@ -20,6 +20,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
+from .engine import bump_weights_epoch
 
 
 def graphs_enabled() -> bool:
@@ -69,6 +70,10 @@ class GraphedTrainStep:
 
     def _fwd_bwd(self) -> Tensor:
         self.opt.zero_grad(set_to_none=True)
+        # The weight banks decide on the HOST whether the normalised operands are current (parameter versions); a captured
+        # graph freezes that decision. Every step must re-normalise (the optimiser moved the weights), so the first
+        # forward of a step always finds its banks invalidated — the later micro-batches of the same step then skip.
+        bump_weights_epoch()
         k = self.accumulate
         if k == 1:
             loss = self.model.training_step((self.x, self.y), 0)

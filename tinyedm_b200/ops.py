@@ -418,24 +418,23 @@ def diffuse(clean: Tensor, eps: Tensor, noise: Tensor, P_mean: float, P_std: flo
     return noisy, sigma
 
 
-def diffuse_philox(clean: Tensor, seed: int, step: Tensor, P_mean: float, P_std: float, sigma_data: float | None):
+def diffuse_philox(clean: Tensor, state: Tensor, P_mean: float, P_std: float, sigma_data: float | None):
     """Diffuser.forward with in-kernel Philox draws; with `sigma_data` also conv_in's im2col operand of c_in * noisy.
-    Returns (noisy, sigma, xcol or None). `step`: device int64 tensor with one element."""
+    Returns (noisy, sigma, xcol or None). `state`: device int64 tensor {seed, step}."""
     B, Ci, H, W = clean.shape
     noisy = torch.empty_like(clean)
     sigma = torch.empty((B,), device=clean.device, dtype=F32)
     xcol = torch.empty((B, H, W, 64), device=clean.device, dtype=BF16) if sigma_data is not None else None
-    _lib.call("tedm_diffuse_philox", clean.data_ptr(), seed & 0xFFFFFFFFFFFFFFFF, step.data_ptr(), P_mean, P_std,
+    _lib.call("tedm_diffuse_philox", clean.data_ptr(), state.data_ptr(), P_mean, P_std,
               float(sigma_data or 0.0), noisy.data_ptr(), sigma.data_ptr(), _p(xcol), B, Ci, H, W, _stream())
     return noisy, sigma, xcol
 
 
-def philox_normal_draws(seed: int, step: Tensor, B: int, n: int):
-    """(eps (B,), noise (B, n)): the draws `diffuse_philox` makes at (seed, step)."""
-    eps = torch.empty((B,), device=step.device, dtype=F32)
-    noise = torch.empty((B, n), device=step.device, dtype=F32)
-    _lib.call("tedm_philox_normal_draws", seed & 0xFFFFFFFFFFFFFFFF, step.data_ptr(), eps.data_ptr(), noise.data_ptr(), B, n,
-              _stream())
+def philox_normal_draws(state: Tensor, B: int, n: int):
+    """(eps (B,), noise (B, n)): the draws `diffuse_philox` makes at state = {seed, step}."""
+    eps = torch.empty((B,), device=state.device, dtype=F32)
+    noise = torch.empty((B, n), device=state.device, dtype=F32)
+    _lib.call("tedm_philox_normal_draws", state.data_ptr(), eps.data_ptr(), noise.data_ptr(), B, n, _stream())
     return eps, noise
 
 

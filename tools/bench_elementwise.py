@@ -104,10 +104,10 @@ for (name, Bq, S, heads, hd) in [("MNIST 14x14 hd 64", 128, 196, 4, 64), ("MNIST
     del qkv
 for (name, Bd, Ci, Hd) in [("CIFAR B=256 3x32x32", 256, 3, 32), ("MNIST B=128 1x28x28", 128, 1, 28), ("ImageNet-latent B=176 4x64x64", 176, 4, 64)]:
     clean = torch.randn(Bd, Ci, Hd, Hd, device=dev)
-    step = torch.zeros(1, dtype=torch.int64, device=dev)
+    step = torch.tensor([1234, 0], dtype=torch.int64, device=dev)
     ni = clean.numel() * 4
     report(f"diffuse_philox + input block {name:30s} r img, w img + 128 B/pixel", 2 * ni + Bd * Hd * Hd * 128,
-           lambda: ops.diffuse_philox(clean, 1234, step, -1.2, 1.2, 0.5))
+           lambda: ops.diffuse_philox(clean, step, -1.2, 1.2, 0.5))
     del clean
 import tinyedm_b200 as T
 ps = [torch.nn.Parameter(torch.randn(35_600_000 // 8, device=dev)) for _ in range(8)]
