@@ -72,7 +72,9 @@ def test_graphed_train_step_matches_eager_step(dev):
             for n, p in params.items():
                 p.copy_(state0[n])
 
+    from tinyedm_b200.engine import bump_weights_epoch
     opt.zero_grad(set_to_none=True)
+    bump_weights_epoch()      # like the captured step: its first forward always re-normalises the weights
     loss_e = m.training_step((clean, labels), 0)
     loss_e.backward()
     g_e = {n: p.grad.clone() for n, p in params.items() if p.grad is not None}

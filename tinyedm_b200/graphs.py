@@ -106,6 +106,8 @@ class GraphedTrainStep:
             loss = self._fwd_bwd()
         self.launches_per_step = _lib.n_calls() - n0 + 1
         self.graph, self.loss = g, loss.detach()   # (capture records, it does not execute: no optimiser step is owed)
+        # the replayed kernels write the gradients into THESE tensors; an eager backward in between would re-bind `.grad`
+        self._grads = [(p, p.grad) for p in self.model.parameters() if p.grad is not None]
 
     def __call__(self, batch) -> Tensor:
         x, y = batch
@@ -116,5 +118,8 @@ class GraphedTrainStep:
         else:
             self.graph.replay()
             loss = self.loss
+            for p, g in self._grads:
+                if p.grad is not g:
+                    p.grad = g
         self.opt.step()
         return loss
