@@ -1,6 +1,7 @@
-"""GPU, >= 2 devices (`-m gpu`; skipped on a single-GPU box): the data-parallel wrapper (bucketed all-reduce of g_hat launched
-from the engine's backward + the trailing small-gradient message) reproduces the single-process gradients of the
-concatenated batch, and batch-sharded sampling reproduces the unsharded result."""
+"""The data-parallel wrapper (bucketed all-reduce of g_hat launched from the engine's backward + the trailing small-gradient
+message, gradient accumulation under no_sync) reproduces the single-process gradients of the concatenated batch, and
+batch-sharded sampling reproduces the unsharded result. Two variants: NCCL on two devices (skipped on a single-GPU box)
+and — so that a one-GPU test run still exercises the whole path on the real engine — two ranks sharing cuda:0 over gloo."""
 import os
 import socket
 
@@ -46,14 +47,18 @@ def _data(dev, n=4):
     return clean, noise, sigma, labels, x0
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, backend="nccl"):
     import torch.distributed as dist
     import tinyedm_b200 as T
     from tinyedm_b200.parallel import DistributedEDM, shard_slice
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    torch.cuda.set_device(rank)
-    dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    index = rank if backend == "nccl" else 0          # gloo: both ranks share device 0 (NCCL refuses duplicate devices)
+    torch.cuda.set_device(index)
+    dev = torch.device("cuda", index)
+    if backend == "nccl":
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         clean, noise, sigma, labels, x0 = _data(dev)
         # single-process reference on the whole batch
@@ -100,6 +105,24 @@ def _worker(rank, world, port, out):
         out.put((rank, worst, serr))
     finally:
         dist.destroy_process_group()
+
+
+def test_data_parallel_gradients_match_single_process_two_ranks_on_one_gpu():
+    """world size 2 over gloo with both ranks on cuda:0: the same engine / bucket / no_sync / finish_backward code as under
+    NCCL, runnable where only one GPU is visible."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out, "gloo")) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    res = sorted(out.get(timeout=5) for _ in range(2))
+    print("gloo on one GPU: rank, worst gradient rel. error vs single process, sharded-sampling rel. error:", res)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")

@@ -239,6 +239,43 @@ def test_small_denoiser_forward_vs_reference_golden(dev, golden):
     assert rel(den.conv_in.weight, dp["conv_in.weight"]) == 0
 
 
+def test_forward_hooks_on_blocks_fire_with_reference_arguments(dev, golden):
+    """activation taps (`register_forward_hook` on EncoderBlock / DecoderBlock — what make_golden.py and
+    wandb-style watchers use) keep working although the blocks run fused: (input, embedding[, skip]) in, block output out,
+    NCHW, equal to the reference's own taps within the accumulated bf16 drift."""
+    cfg = SMALL
+    dp, ep, _ = small_params()
+    den, emb_m, _ = build_modules(cfg, dp, ep, None, dev)
+    den.eval(); emb_m.eval()
+    seen = {}
+    def tap(name):
+        def hook(mod, args, out):
+            seen[name] = (tuple(a.shape for a in args), out.float().clone())
+        return hook
+    handles = [den.encoder_blocks[1].register_forward_hook(tap("encoder_blocks.1")),
+               den.decoder_blocks[2].register_forward_hook(tap("decoder_blocks.2")),
+               den.decoder_blocks[3].register_forward_hook(tap("decoder_blocks.3"))]
+    noisy = torch.from_numpy(golden["noisy"]).to(dev)
+    sigma = torch.from_numpy(golden["sigma"]).to(dev)
+    labels = torch.from_numpy(golden["labels"]).to(dev)
+    with torch.no_grad():
+        _, e = emb_m(sigma, labels)
+        den(noisy, sigma, e)
+    assert set(seen) == {"encoder_blocks.1", "decoder_blocks.2", "decoder_blocks.3"}
+    for name, (shapes, out) in seen.items():
+        ref = golden["tap/" + name].astype(np.float32)
+        assert out.shape == ref.shape and rel(out, ref) < DRIFT_TOL, name
+        assert shapes[1] == tuple(e.shape)
+    assert len(seen["encoder_blocks.1"][0]) == 2 and len(seen["decoder_blocks.2"][0]) == 3     # the skip block gets (x, emb, skip)
+    assert len(seen["decoder_blocks.3"][0]) == 2
+    for h in handles:
+        h.remove()
+    seen.clear()
+    with torch.no_grad():
+        den(noisy, sigma, e)
+    assert not seen
+
+
 def test_small_denoiser_teacher_forced_blocks(dev, golden):
     """Per-layer criterion: every block fed the ORACLE's (bf16-rounded) input must match the oracle's output <= 1e-2."""
     cfg = SMALL

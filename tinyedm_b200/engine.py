@@ -269,6 +269,7 @@ class BlockPlan:
     in_src: int = -1      # index into the skip list that is this block's input (if its input is a skip source)
     w: dict = field(default_factory=dict)  # name -> WeightSlot
     gain: torch.nn.Parameter | None = None
+    module: torch.nn.Module | None = None  # the EncoderBlock / DecoderBlock that owns the parameters (forward hooks)
 
 
 def fused_skip_mean_enabled() -> bool:
@@ -331,6 +332,7 @@ class DenoiserEngine:
                 bp.w["out"] = conv_slot(pre + "attention.out_conv.weight", blk.attention.out_conv.weight)
             bp.w["embed"] = f32_slot(pre + "embed.weight", blk.embed.weight)
             bp.gain = blk.gain
+            bp.module = blk
             bp.col0 = col
             bp.index = idx
             col += bp.cout
@@ -475,7 +477,16 @@ class DenoiserEngine:
                 skip = skips.pop()
                 mean = means.pop()
             want_mean = bp.kind == "enc" and used[n_pushed]
+            x_in = x
             x, saved, out_mean = self._block_forward(bp, x, skip, mod, mod_stride, drop_p, save, mean, want_mean, seed_t)
+            if bp.module is not None and bp.module._forward_hooks:
+                # The block ran fused, not through its module's __call__: forward hooks registered on the EncoderBlock /
+                # DecoderBlock (activation logging, `wandb.watch`-style taps) still fire, with the reference's argument
+                # order (input, embedding[, skip]) and the block output as NCHW views of the bf16 NHWC tensors
+                nchw = lambda t: t.permute(0, 3, 1, 2)
+                hook_args = (nchw(x_in), emb) + ((nchw(skip),) if skip is not None else ())
+                for hook in list(bp.module._forward_hooks.values()):
+                    hook(bp.module, hook_args, nchw(x))
             if bp.kind == "enc":
                 skips.append(x)
                 means.append(out_mean)

@@ -30,7 +30,10 @@ from .ops import BF16, F32
 # weight holders
 # ---------------------------------------------------------------------------------------------------------
 class _FusedOnly(nn.Module):
-    """Parameter holder whose arithmetic is executed by the enclosing Denoiser's fused plan."""
+    """Parameter holder whose arithmetic is executed by the enclosing Denoiser's fused plan. Forward hooks registered on
+    an EncoderBlock / DecoderBlock are fired by the engine with (input, embedding[, skip]) and the block's output
+    (engine.DenoiserEngine.forward); the finer-grained holders (attention, ScaleLong, resamplers) have no separate
+    activations to show — their arithmetic lives in epilogues."""
 
     def forward(self, *args, **kwargs):
         raise RuntimeError(
