@@ -93,7 +93,12 @@ def test_skip_mean_from_conv_epilogue_matches_channel_dot(dev, B, monkeypatch):
         monkeypatch.setenv("TEDM_FUSED_SKIP_MEAN", "0")
         d0 = model(x, sigma, y).clone()
     assert torch.equal(d1, d1b)
-    assert rel(d1, d0) < 4e-3, rel(d1, d0)   # two equally valid bf16 paths (measured 1.6-2.0e-3)
+    # Self-consistency of two equally valid bf16 paths, NOT a parity claim: the means differ in summation order (fixed-order
+    # partial sums vs one CTA per channel group), which moves a few bf16 roundings downstream; measured 1.6-2.0e-3, once
+    # 2.015e-3 — hence 4e-3 rather than the 2e-3 this assert started with. Parity of the fused mean itself is pinned
+    # against fp32 torch arithmetic in test_colsum_partials_equal_the_column_sums (<= 1e-5), and the networks that use it
+    # against the oracle in tests/test_gpu_parity.py / test_gpu_block_parity.py.
+    assert rel(d1, d0) < 4e-3, rel(d1, d0)
 
 
 def test_colsum_partials_equal_the_column_sums(dev):
