@@ -58,7 +58,9 @@ int tedm_weight_prep_backward(const tedm_weight_desc* table, int n, int total_ro
  *             Philox stream keyed by seed (+ *seed_ptr, an optional DEVICE step counter so that a captured CUDA graph
  *             draws a fresh mask on every replay)
  *           2 axpby: out = alpha*conv + beta*res; mp_add(x, conv, t) is alpha = t/c, beta = (1-t)/c,
- *             c = sqrt((1-t)^2+t^2)                                                     (networks.py:87-88, :263, :327)
+ *             c = sqrt((1-t)^2+t^2)                                                     (networks.py:87-88, :263, :327).
+ *             With nrm (eps + rms per pixel): res is the UN-normalised block input and enters as res / nrm[pixel],
+ *             i.e. the pixel-normalised residual of an encoder block (networks.py:249, :263) without storing it
  *         Backward epilogues (the call is then the DATA GRADIENT of a conv, `conv` = alpha * dgrad):
  *           3 adjoint of epilogue 1 fused into the dgrad of conv_3x3_2: conv = dL/dh; out = dL/draw;
  *             d_mod[b,c] += sum_pixels (needs aux = raw, mod, d_mod zeroed by the caller, the same seed/seed_ptr)

@@ -70,6 +70,12 @@ def test_pair_conv_epilogues_vs_torch(dev, B, H, W, Cin, Cout, ks):
     res = torch.randn(B, H, W, Cout, device=dev).to(BF)
     y = ops.conv2d(x, wq, ks, Cout, epi=EPI_AXPBY, alpha=0.4, beta=0.9, res=res)
     assert rel(y, 0.4 * acc + 0.9 * res.float()) < 6e-3
+    # mp_add whose residual is the UN-normalised block input, divided by its pixel norm in the epilogue (networks.py:249, :263)
+    rn = (torch.rand(B, H, W, device=dev) + 0.5).contiguous()
+    want_n = 0.4 * acc + 0.9 * res.float() / rn[..., None]
+    y = ops.conv2d(x, wq, ks, Cout, epi=EPI_AXPBY, alpha=0.4, beta=0.9, res=res, nrm=rn)
+    assert rel(y, want_n) < 6e-3
+    assert rel(ops.conv2d(x, wq, ks, Cout, epi=EPI_AXPBY, alpha=0.4, beta=0.9, res=res, nrm=rn, block_n=bn_single), want_n) < 6e-3
     # modulation * mp_silu (+ raw copy), no dropout
     mod = (torch.randn(B, Cout, device=dev) * 0.3 + 1).contiguous()
     raw = torch.zeros(B, H, W, Cout, device=dev, dtype=BF)

@@ -392,8 +392,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           } else if constexpr (EPI == EPI_AXPBY) {
             float rv[CW];
             row_load<CW>(p.res + row_off + c0, rv);
+            const float rs = p.nrm != nullptr ? p.beta / p.nrm[pix] : p.beta;   // nrm: res is the un-normalised tensor
 #pragma unroll
-            for (int i = 0; i < CW; ++i) v[i] += p.beta * rv[i];
+            for (int i = 0; i < CW; ++i) v[i] += rs * rv[i];
           } else if constexpr (EPI == EPI_SILU_BWD) {
             // g_x = alpha*acc * mp_silu'(x) + beta*res, [pixel-norm adjoint], (+ what is already in `out`)
             float xv[CW];
@@ -506,13 +507,13 @@ static int conv_pair_mode() {
 }
 
 bool conv_split_supported(const ConvGemmArgs& a) {
-  return conv_pair_mode() == 1 && a.B > 0 && a.nrm == nullptr && a.split_c > 0 && a.split_c % 64 == 0 && a.split_c < a.Cout &&
+  return conv_pair_mode() == 1 && a.B > 0 && a.nrm == nullptr && a.epi == EPI_SILU_BWD && a.split_c > 0 && a.split_c % 64 == 0 && a.split_c < a.Cout &&
          conv_pair_supported(a);
 }
 
 static bool conv_takes_pair(const ConvGemmArgs& a) {
   return a.block_n_override == 0 && conv_pair_mode() == 1 && a.B > 0 && conv_pair_supported(a) &&
-         (a.nrm != nullptr || 4 * conv_pair_tiles(a) > num_sms());   // at least half of the CTA pairs get a tile
+         ((a.epi == EPI_SILU_BWD && a.nrm != nullptr) || 4 * conv_pair_tiles(a) > num_sms());   // at least half of the CTA pairs get a tile
 }
 
 int conv_colsum_slots(const ConvGemmArgs& a) {
@@ -550,7 +551,7 @@ int conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t stream) {
     for (int i = 0; i < 3; ++i) {
       const int c = cands[i];
       if (c > 64 && a.Cout <= c / 2) continue;                 // would waste more than half of the tile
-      if (a.nrm != nullptr && a.Cout > c) continue;            // fused pixel-norm adjoint needs one N tile
+      if (a.epi == EPI_SILU_BWD && a.nrm != nullptr && a.Cout > c) continue;   // fused pixel-norm adjoint needs one N tile
       const long long tiles = (long long)p.m_tiles * ((a.Cout + c - 1) / c);
       const long long waves = (tiles + num_sms() - 1) / num_sms();
       const long long cost = waves * (c + 48);
@@ -572,7 +573,7 @@ int conv_gemm_launch(const ConvGemmArgs& a, cudaStream_t stream) {
     TEDM_CHECK(a.mod != nullptr && a.aux != nullptr && a.d_mod != nullptr, "conv_gemm: MODSILU_BWD epilogue needs mod, raw and d_mod");
   if (a.epi == EPI_SILU_BWD) {
     TEDM_CHECK(a.aux != nullptr, "conv_gemm: SILU_BWD epilogue needs x");
-    TEDM_CHECK(a.nrm == nullptr || a.Cout <= 256, "conv_gemm: fused pixel-norm adjoint needs Cout <= 256 (one N tile)");
+    TEDM_CHECK(a.nrm == nullptr || a.epi != EPI_SILU_BWD || a.Cout <= 256, "conv_gemm: fused pixel-norm adjoint needs Cout <= 256 (one N tile)");
   }
   TEDM_CHECK(a.Cout % 32 == 0 || a.epi == EPI_PLAIN || a.epi == EPI_AXPBY || a.epi == EPI_MODSILU,
              "conv_gemm: backward epilogues need Cout %% 32 == 0");

@@ -399,6 +399,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int b = 0;
     uint32_t t_row = 0;
     float dot = 0.f, inv_n = 1.f, kk = 0.f;
+    float res_scale = 1.f;  // AXPBY with nrm: the residual operand is the UN-normalised tensor, scaled by 1/nrm of its pixel
 
     int cur_mt = 0;         // M tile of this CTA within the current pair tile
     // column sums over this warp's 32 rows of the values as stored (bf16), fixed order: see ConvGemmArgs::col_partial
@@ -426,6 +427,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tc_fence_after();
         t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kBN;
         dot = 0.f;
+        if (EPI == EPI_AXPBY && p.nrm != nullptr) res_scale = valid ? p.beta / p.nrm[pix] : 0.f;
+        else res_scale = p.beta;
       }
       if (pos.cb < pos.ce) {
         const bool sweep1 = two_sweep && pos.pass == 0;   // accumulates the row dot, parks v in TMEM, writes nothing
@@ -478,7 +481,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               float rv[CW];
               srow_load<CW>(buf0, m, j0, rv);
 #pragma unroll
-              for (int i = 0; i < CW; ++i) v[i] += p.beta * rv[i];
+              for (int i = 0; i < CW; ++i) v[i] += res_scale * rv[i];
               srow_store<CW>(obuf, m, j0, v);
             }
             if (p.col_partial != nullptr) col_sums(v, cc);
@@ -794,7 +797,7 @@ int launch_pair(const CUtensorMap* maps, const ConvGemmParams& p, int clusters, 
 bool conv_pair_supported(const ConvGemmArgs& a) {
   if (a.ksize != 1 && a.ksize != 3) return false;
   if (a.Cin % 64 != 0 || a.Cout % 64 != 0 || a.Cout < 128) return false;
-  if (a.nrm != nullptr && a.Cout > kBN) return false;
+  if (a.epi == EPI_SILU_BWD && a.nrm != nullptr && a.Cout > kBN) return false;   // fused pixel-norm adjoint: one N tile
   int RH, NB;
   if (conv_tile_geometry(a.H, a.W, &RH, &NB) != 0) return false;
   return true;
@@ -870,7 +873,8 @@ int conv_pair_launch(const ConvGemmArgs& a, cudaStream_t stream) {
   p.split_from = p.work_items = pair_tiles;
   const int rem = pair_tiles % clusters;
   static const bool tail_split = [] { const char* e = getenv("TEDM_CONV_TAIL_SPLIT"); return !(e != nullptr && e[0] == '0'); }();
-  if (tail_split && rem > 0 && 2 * rem <= clusters && pair_tiles > clusters && a.Cout % kBN == 0 && a.nrm == nullptr) {
+  if (tail_split && rem > 0 && 2 * rem <= clusters && pair_tiles > clusters && a.Cout % kBN == 0 &&
+      !(a.epi == EPI_SILU_BWD && a.nrm != nullptr)) {
     p.split_from = pair_tiles - rem;
     p.work_items = pair_tiles + rem;
   }

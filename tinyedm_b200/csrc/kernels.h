@@ -41,7 +41,9 @@ struct ConvGemmArgs {
   int block_n_override;      // 0 = heuristic
   const __nv_bfloat16* aux;  // MODSILU_BWD: raw conv output; SILU_BWD: x          (B,H,W,Cout)
   float* d_mod;              // MODSILU_BWD: (B, mod_stride) fp32, column offset applied, accumulated atomically
-  const float* nrm;          // SILU_BWD: (B*H*W) eps + rms of the pixel norm whose adjoint is fused, or null
+  const float* nrm;          // SILU_BWD: (B*H*W) eps + rms of the pixel norm whose adjoint is fused, or null.
+                             // AXPBY: when given, `res` is the UN-normalised tensor and enters as res / nrm[pixel]
+                             // (the pixel-normalised residual of an encoder block without ever storing it)
   int accumulate_out;        // SILU_BWD: out += result
   // SILU_BWD, CTA-pair kernel only: split the Cout = split_c + C2 output channels of a decoder block's concatenated
   // input gradient in the epilogue. Channels < split_c go to `out` ((B,H,W,split_c), accumulate_out applies to it);

@@ -543,8 +543,14 @@ class DenoiserEngine:
         S: dict = {}
         B, Hin, Win, _ = xin.shape
         S["in_shape"] = (B, Hin, Win)
+        res_nrm = None
         if bp.kind == "enc":
-            if "conv_1x1" not in bp.w:
+            if "conv_1x1" not in bp.w and bp.resample == RESAMPLE_NONE and not save:
+                # inference: x = pixel_norm(xin) is never stored — only mp_silu(x) and the per-pixel norm; conv_3x3_2's
+                # mp_add epilogue takes the residual as xin / nrm (one activation-sized write less per encoder block)
+                _, a, res_nrm = ops.block_prep(xin, pixelnorm=True, want_x=False, want_nrm=True)
+                x, nrm = xin, None
+            elif "conv_1x1" not in bp.w:
                 x, a, nrm = ops.block_prep(xin, resample=bp.resample, pixelnorm=True, want_nrm=save)
             else:
                 r = xin
@@ -574,7 +580,7 @@ class DenoiserEngine:
                        mod_stride=mod_stride, drop_p=drop_p, seed=0x5EED0000 + bp.index,
                        seed_ptr=seed_t if seed_t is not None else self.step_counter, raw=raw)
         out, out_mean = self._conv_with_mean(h, bp.w["conv_3x3_2"].fwd, 3, bp.cout, want_mean and not bp.attn, epi=EPI_AXPBY,
-                                             alpha=wb, beta=wa, res=xr)
+                                             alpha=wb, beta=wa, res=xr, nrm=res_nrm)
         if save:
             S.update(x=x, a=a, raw=raw, h=h)
         if bp.attn:
