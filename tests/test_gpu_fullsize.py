@@ -15,6 +15,13 @@ pytestmark = pytest.mark.gpu
 BF = torch.bfloat16
 
 
+def _eager(solver, model, x0, labels):
+    """The solver's eager loop exactly as `solve` runs it (under no_grad: with gradients enabled the Denoiser takes its
+    training-style path, which stores the pixel-normalised block inputs and is not bit-identical to the inference path)."""
+    with torch.no_grad():
+        return solver._solve_eager(model, x0, labels)
+
+
 @pytest.fixture(scope="module")
 def dev():
     if not torch.cuda.is_available():
@@ -96,11 +103,11 @@ def test_full_size_sampler_is_deterministic_and_graph_replay_matches_eager(dev):
     x0 = torch.randn(128, 3, 32, 32, generator=g).to(dev)
     labels = torch.randint(0, 10, (128, 1), generator=g).to(dev)
     solver = T.DeterministicSolver(num_steps=32)
-    eager = solver._solve_eager(model, x0, labels)
+    eager = _eager(solver, model, x0, labels)
     a = solver.solve(model, x0, labels)      # captures the 63-evaluation trajectory
     b = solver.solve(model, x0, labels)      # replays it
     assert torch.isfinite(a).all()
     assert torch.equal(a, eager) and torch.equal(b, eager)
     # batch sharding (how the 8 GPUs split the work) does not change an image: the network has no cross-sample op
-    half = solver._solve_eager(model, x0[:64].contiguous(), labels[:64].contiguous())
+    half = _eager(solver, model, x0[:64].contiguous(), labels[:64].contiguous())
     assert rel(half, eager[:64]) < 2e-2      # different tile shapes -> different bf16 summation order, not bit-identical

@@ -7,6 +7,13 @@ from tests.helpers import SMALL, build_modules, rel, small_params
 pytestmark = pytest.mark.gpu
 
 
+def _eager(solver, model, x0, labels):
+    """The solver's eager loop exactly as `solve` runs it (under no_grad: with gradients enabled the Denoiser takes its
+    training-style path, which stores the pixel-normalised block inputs and is not bit-identical to the inference path)."""
+    with torch.no_grad():
+        return solver._solve_eager(model, x0, labels)
+
+
 @pytest.fixture(scope="module")
 def dev():
     if not torch.cuda.is_available():
@@ -27,7 +34,7 @@ def test_sampler_graph_replay_is_bit_identical_to_eager(dev, golden):
     x0 = torch.from_numpy(golden["x0"]).to(dev)
     labels = torch.from_numpy(golden["labels"]).to(dev)
     solver = T.DeterministicSolver(num_steps=6)
-    eager = solver._solve_eager(model, x0.float().contiguous(), labels)
+    eager = _eager(solver, model, x0.float().contiguous(), labels)
     first = solver.solve(model, x0, labels)            # captures
     ent = next(iter(solver._graphs.values()))
     assert ent.get("graph") is not None, ent.get("error")
@@ -35,13 +42,13 @@ def test_sampler_graph_replay_is_bit_identical_to_eager(dev, golden):
     assert torch.equal(first, eager) and torch.equal(again, eager)
     # different inputs through the same graph
     x1 = torch.randn_like(x0)
-    assert torch.equal(solver.solve(model, x1, labels), solver._solve_eager(model, x1.float().contiguous(), labels))
+    assert torch.equal(solver.solve(model, x1, labels), _eager(solver, model, x1.float().contiguous(), labels))
     # a parameter update must reach the replayed graph (weights are re-normalised outside the graph)
     with torch.no_grad():
         model.denoiser.encoder_blocks[0].conv_3x3_1.weight.mul_(-1.0)
     changed = solver.solve(model, x0, labels)
     assert not torch.equal(changed, eager)
-    assert torch.equal(changed, solver._solve_eager(model, x0.float().contiguous(), labels))
+    assert torch.equal(changed, _eager(solver, model, x0.float().contiguous(), labels))
 
 
 def test_graphed_train_step_matches_eager_step(dev):
