@@ -56,8 +56,10 @@ class _ConvFn(torch.autograd.Function):
 class Conv2d(nn.Module):
     """MPConv: force-normalised stride-1 'same' convolution, no bias (networks.py:22-43).
 
-    Inside a Denoiser it is only a weight holder. Called on its own (it is part of the reference's public
-    exports) it runs the same tensor-core kernel on an NCHW tensor; the NCHW<->NHWC relayout is torch plumbing.
+    Inside a Denoiser it is only a weight holder. Called on its own (it is part of the reference's public exports) it runs
+    the same tensor-core kernel on an NCHW tensor; the NCHW<->NHWC relayout is torch plumbing. Channel counts that are
+    not multiples of 64 (e.g. ScaleLong's 257 -> 16, networks.py:109-110) are zero-padded to the next multiple around the
+    kernel: the weight bank then emits the fp32 w_hat in parameter layout and the padded bf16 operands are laid out here.
     """
 
     def __init__(self, in_channels, out_channels, kernel_size):
@@ -66,37 +68,77 @@ class Conv2d(nn.Module):
         self.weight = nn.Parameter(torch.randn(out_channels, in_channels, kernel_size, kernel_size))
         self._bank: WeightBank | None = None
 
+    @property
+    def _padded(self) -> bool:
+        return self.in_channels % 64 != 0 or self.out_channels % 64 != 0
+
     def _prepared(self, dev):
-        if self.kernel_size not in (1, 3) or self.in_channels % 64 or self.out_channels % 64:
-            raise RuntimeError("tinyedm_b200.Conv2d (standalone): kernel 1|3 and channels % 64 == 0 are required")
+        if self.kernel_size not in (1, 3):
+            raise RuntimeError("tinyedm_b200.Conv2d (standalone): kernel size 1 or 3 is required")
         ops.ensure_device(dev)
         if self._bank is None or self._bank.slots[0].param is not self.weight:
-            self._bank = WeightBank([conv_slot("weight", self.weight)])
+            self._bank = WeightBank([f32_slot("weight", self.weight) if self._padded else conv_slot("weight", self.weight)])
         if self._bank.device != dev:
             self._bank.materialise(dev)
         self._bank.prepare(self.training)
         return self._bank.slots[0]
 
+    def _padded_operands(self, slot):
+        """bf16 forward [Cout_p][tap][Cin_p] and data-gradient [Cin_p][tap flipped][Cout_p] operands from the fp32 w_hat."""
+        k, ci, co = self.kernel_size, self.in_channels, self.out_channels
+        cip, cop = (ci + 63) // 64 * 64, (co + 63) // 64 * 64
+        w_hat = slot.f32.view(co, ci, k, k)
+        wp = torch.zeros((cop, cip, k, k), device=w_hat.device, dtype=F32)
+        wp[:co, :ci] = w_hat
+        fwd = wp.permute(0, 2, 3, 1).reshape(cop, k * k * cip).to(BF16).contiguous()
+        dgrad = wp.flip(2, 3).permute(1, 2, 3, 0).reshape(cip, k * k * cop).to(BF16).contiguous()
+        return fwd, dgrad, cip, cop
+
     def _run(self, x: Tensor):
         slot = self._prepared(x.device)
-        xh = x.permute(0, 2, 3, 1).to(BF16).contiguous()
-        y = ops.conv2d(xh, slot.fwd, self.kernel_size, self.out_channels)
-        return y.permute(0, 3, 1, 2).to(x.dtype if x.dtype in (BF16, torch.float16) else BF16), (xh, x.dtype)
+        out_dtype = x.dtype if x.dtype in (BF16, torch.float16) else BF16
+        xh = x.permute(0, 2, 3, 1).to(BF16)
+        if not self._padded:
+            xh = xh.contiguous()
+            y = ops.conv2d(xh, slot.fwd, self.kernel_size, self.out_channels)
+            return y.permute(0, 3, 1, 2).to(out_dtype), (xh, x.dtype, None)
+        fwd, dgrad, cip, cop = self._padded_operands(slot)
+        xp = torch.zeros(xh.shape[:3] + (cip,), device=x.device, dtype=BF16)
+        xp[..., :self.in_channels] = xh
+        y = ops.conv2d(xp, fwd, self.kernel_size, cop)[..., :self.out_channels]
+        return y.permute(0, 3, 1, 2).to(out_dtype), (xp, x.dtype, (dgrad, cip, cop))
 
     def _run_backward(self, saved, gy: Tensor, need_gx: bool):
-        xh, in_dtype = saved
+        xh, in_dtype, pad = saved
         bank = self._bank
         bank.begin_backward()
         slot = bank.slots[0]
-        gh = gy.permute(0, 2, 3, 1).to(BF16).contiguous()
-        ops.conv2d_wgrad(gh, xh, slot.ghat, self.kernel_size)
+        k, ci, co = self.kernel_size, self.in_channels, self.out_channels
+        gh = gy.permute(0, 2, 3, 1).to(BF16)
+        if pad is None:
+            gh = gh.contiguous()
+            ops.conv2d_wgrad(gh, xh, slot.ghat, k)
+            bank.backward()
+            gx = None
+            if need_gx:
+                gx = ops.conv2d(gh, slot.dgrad, k, ci).permute(0, 3, 1, 2).to(in_dtype)
+            return gx, bank.autograd_grads()[0]
+        dgrad, cip, cop = pad
+        gp = torch.zeros(gh.shape[:3] + (cop,), device=gy.device, dtype=BF16)
+        gp[..., :co] = gh
+        dw = torch.zeros((cop, k * k, cip), device=gy.device, dtype=F32)
+        ops.conv2d_wgrad(gp, xh, dw, k)
+        # dL/dw_hat back in parameter layout (Cout, Cin, k, k) for the weight-norm Jacobian
+        slot.ghat.copy_(dw.view(cop, k, k, cip)[:co, :, :, :ci].permute(0, 3, 1, 2).reshape(co, ci * k * k))
         bank.backward()
         gx = None
         if need_gx:
-            gx = ops.conv2d(gh, slot.dgrad, self.kernel_size, self.in_channels).permute(0, 3, 1, 2).to(in_dtype)
+            gx = ops.conv2d(gp, dgrad, k, cip)[..., :ci].permute(0, 3, 1, 2).to(in_dtype)
         return gx, bank.autograd_grads()[0]
 
     def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("tinyedm_b200.Conv2d runs on CUDA (sm_100a) only; there is no CPU fallback")
         return _ConvFn.apply(x, self.weight, self)
 
     def extra_repr(self) -> str:
