@@ -587,7 +587,13 @@ class DenoiserEngine:
             c5 = 1.0 / math.sqrt(2.0)
             qkv = ops.conv2d(out, bp.w["qkv"].fwd, 1, 3 * bp.cout)
             heads = self.m.num_heads
-            if ops.attention_specialised(qkv.shape[1] * qkv.shape[2], bp.cout // heads) or not generic_attention_enabled():
+            S_att = qkv.shape[1] * qkv.shape[2]
+            specialised = ops.attention_specialised(S_att, bp.cout // heads)
+            if specialised and save and S_att == 64 and os.environ.get("TEDM_ATTN_S64_GENERIC", "1") != "0":
+                # training at S = 64 (CIFAR 8x8): the packed generic backward (two (image, head) pairs per tile, two CTAs per
+                # SM) beats the specialised two-kernel one by more than the normalisation pass costs the forward
+                specialised = False
+            if specialised or not generic_attention_enabled():
                 y, lse = ops.attention_forward(qkv, heads, need_lse=save)      # normalises q, k, v inside the kernel
                 if save:
                     S.update(qkv=qkv)
