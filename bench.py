@@ -390,6 +390,11 @@ def bench_train_config(cx: Ctx, T, name: str, steps: int, warmup: int, *, use_un
         loss_host[i % steps].copy_(loss.detach(), non_blocking=True)
     for i in range(warmup):
         step(i)
+    settle = 0
+    if wl["fwd_gflop"] * B * k < 5e4:        # short steps (CIFAR, MNIST): ~1 s of continuous load before the timed region
+        settle = 48                           # (see run_b200: power-cap transient after the idle time of graph capture)
+        for i in range(settle):
+            step(i)
     ms = cx.timed(step, steps)
     imgs = cx.world * B * k * steps
     value = imgs / (ms / 1e3)
@@ -401,7 +406,7 @@ def bench_train_config(cx: Ctx, T, name: str, steps: int, warmup: int, *, use_un
            "images_per_optimizer_step": cx.world * B * k, "steps": steps, "image": f"{C}x{H}x{W}",
            "params_M": sum(p.numel() for p in model.parameters()) / 1e6, "use_uncertainty": bool(use_uncertainty),
            "tflops_per_gpu": tf, "frac_of_bf16_sustained": tf / peak_tf, "final_loss": float(loss_host[(steps - 1) % steps]),
-           "launch": "CUDA graph replay" if gstep.graph is not None else f"eager ({gstep.error})",
+           "launch": "CUDA graph replay" if gstep.graph is not None else f"eager ({gstep.error})", "settle_steps": settle,
            "gpu_launches_per_step": gstep.launches_per_step, "input": "pinned host batch -> device inside the timed region",
            "h2d_bytes_per_step": B * k * (C * H * W * 4 + 8), "d2h_bytes_per_step": 4}
     del gstep, opt, ddp, model
@@ -569,17 +574,17 @@ def run_b200(args) -> None:
     for i in range(args.warmup):
         run_step((dev_imgs[i % n_pool], dev_lbls[i % n_pool]))
     torch.cuda.synchronize()
-    # Settle: graph capture leaves the GPU idle for a moment, and the first ~0.5 s of back-to-back steps then run through
-    # the power-cap controller's transient (boost, overshoot, recover: the first 30 steps measured 2-4 % slower than the
-    # same step a second later in the same process). A fixed number of untimed steps (~1.4 s of continuous load) puts the
-    # timed region into the steady state a training job lives in (MEASURED_PEAKS' sustained figure is taken the same way).
+    t_wait = time.time()
+    while clocks.mark() == 0 and time.time() - t_wait < 3.0:     # nvidia-smi needs a moment for its first sample
+        time.sleep(0.05)
+    # Settle: graph capture and the wait above leave the GPU idle, and the first ~0.5 s of back-to-back steps after an idle
+    # period run through the power-cap controller's transient (the first timed region used to read 1-4 % slower than the
+    # e2e region that follows it without a pause, although that one also copies its batch from the host). A fixed number
+    # of untimed steps of continuous load directly before the timed region puts it into the steady state a training job
+    # lives in (MEASURED_PEAKS' sustained figure is taken the same way).
     settle_steps = max(0, args.settle_steps)      # a COUNT, identical on every rank (each step holds collectives)
     for i in range(settle_steps):
         run_step((dev_imgs[i % n_pool], dev_lbls[i % n_pool]))
-    torch.cuda.synchronize()
-    t_wait = time.time()
-    while clocks.mark() == 0 and time.time() - t_wait < 3.0:
-        time.sleep(0.05)
     c0 = clocks.mark()
     with LaunchCounter(_lib) as lc:
         ms_dev = timed(lambda i: run_step((dev_imgs[i % n_pool], dev_lbls[i % n_pool])), args.steps)
