@@ -390,11 +390,6 @@ def bench_train_config(cx: Ctx, T, name: str, steps: int, warmup: int, *, use_un
         loss_host[i % steps].copy_(loss.detach(), non_blocking=True)
     for i in range(warmup):
         step(i)
-    settle = 0
-    if wl["fwd_gflop"] * B * k < 5e4:        # short steps (CIFAR, MNIST): ~1 s of continuous load before the timed region
-        settle = 48                           # (see run_b200: power-cap transient after the idle time of graph capture)
-        for i in range(settle):
-            step(i)
     ms = cx.timed(step, steps)
     imgs = cx.world * B * k * steps
     value = imgs / (ms / 1e3)
@@ -406,7 +401,7 @@ def bench_train_config(cx: Ctx, T, name: str, steps: int, warmup: int, *, use_un
            "images_per_optimizer_step": cx.world * B * k, "steps": steps, "image": f"{C}x{H}x{W}",
            "params_M": sum(p.numel() for p in model.parameters()) / 1e6, "use_uncertainty": bool(use_uncertainty),
            "tflops_per_gpu": tf, "frac_of_bf16_sustained": tf / peak_tf, "final_loss": float(loss_host[(steps - 1) % steps]),
-           "launch": "CUDA graph replay" if gstep.graph is not None else f"eager ({gstep.error})", "settle_steps": settle,
+           "launch": "CUDA graph replay" if gstep.graph is not None else f"eager ({gstep.error})",
            "gpu_launches_per_step": gstep.launches_per_step, "input": "pinned host batch -> device inside the timed region",
            "h2d_bytes_per_step": B * k * (C * H * W * 4 + 8), "d2h_bytes_per_step": 4}
     del gstep, opt, ddp, model
@@ -577,11 +572,8 @@ def run_b200(args) -> None:
     t_wait = time.time()
     while clocks.mark() == 0 and time.time() - t_wait < 3.0:     # nvidia-smi needs a moment for its first sample
         time.sleep(0.05)
-    # Settle: graph capture and the wait above leave the GPU idle, and the first ~0.5 s of back-to-back steps after an idle
-    # period run through the power-cap controller's transient (the first timed region used to read 1-4 % slower than the
-    # e2e region that follows it without a pause, although that one also copies its batch from the host). A fixed number
-    # of untimed steps of continuous load directly before the timed region puts it into the steady state a training job
-    # lives in (MEASURED_PEAKS' sustained figure is taken the same way).
+    # Optional untimed extra steps directly before the timed region (--settle-steps). Measured A/B on one box: 0 vs 64 steps
+    # gave 11 754 vs 11 700 img/s — there is no power-cap transient to wait out, so the default is 0.
     settle_steps = max(0, args.settle_steps)      # a COUNT, identical on every rank (each step holds collectives)
     for i in range(settle_steps):
         run_step((dev_imgs[i % n_pool], dev_lbls[i % n_pool]))
@@ -724,8 +716,7 @@ def run_b200(args) -> None:
                        "weights": "random init, gain_out=1", "dropout": 0.13,
                        "lr": f"0.02 x {LR_RAMP} (the ramp-up region of the reference's schedule, edm.py:306-317; no work skipped)",
                        "settle_steps": settle_steps,
-                       "settle": f"{settle_steps} further untimed steps of continuous load after the {args.warmup} warm-up steps, so "
-                                 "that the timed region is past the power-cap transient",
+
                        "launch": "CUDA graph replay of fwd+bwd (GraphedTrainStep) + 1 optimiser launch" if graph_mode
                                  else "eager (one C-ABI call per kernel)"},
             "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": B * 3 * 32 * 32 * 4 + B * 8,
@@ -751,7 +742,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--headline-only", action="store_true", help="skip the other BASELINE configs (MNIST / ImageNet-latent / uncertainty)")
     ap.add_argument("--eager", action="store_true", help="time the eager step instead of the CUDA-graph replay")
-    ap.add_argument("--settle-steps", type=int, default=64, help="untimed steps of continuous load before the timed region")
+    ap.add_argument("--settle-steps", type=int, default=0, help="extra untimed steps directly before the timed region")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
