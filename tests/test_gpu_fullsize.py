@@ -111,3 +111,54 @@ def test_full_size_sampler_is_deterministic_and_graph_replay_matches_eager(dev):
     # batch sharding (how the 8 GPUs split the work) does not change an image: the network has no cross-sample op
     half = _eager(solver, model, x0[:64].contiguous(), labels[:64].contiguous())
     assert rel(half, eager[:64]) < 2e-2      # different tile shapes -> different bf16 summation order, not bit-identical
+
+
+def test_full_size_forward_backward_vs_fp32_oracle_on_the_gpu(dev):
+    """BASELINE.json's own training batch (256 x 3 x 32 x 32, the 35.6 M CIFAR net), element-wise: D, the loss and the
+    gradient of every parameter tensor against the fp32 oracle evaluated ON THE GPU with TF32 off (seconds instead of the
+    CPU's minutes). Eval mode / no dropout so that both sides see the same weights and masks; the bounds are the
+    accumulated-drift bounds of the small-batch config tests (tests/test_gpu_parity.py)."""
+    import tinyedm_b200 as T
+    from oracle import edm2_oracle as O
+    from tests.helpers import build_modules, cifar_cfg, seeded_params
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = cifar_cfg(num_classes=None)
+    dp, ep, _ = seeded_params(cfg, seed=17)
+    den, emb_m, _ = build_modules(cfg, dp, ep, None, dev)
+    den.eval(); emb_m.eval()
+    B = 256
+    g = torch.Generator().manual_seed(6)
+    clean = (0.5 * torch.randn(B, 3, 32, 32, generator=g)).clamp(-1, 1).to(dev)
+    sigma = torch.exp(torch.randn(B, generator=g) * 1.2 - 1.2).to(dev)
+    noisy = clean + torch.randn(B, 3, 32, 32, generator=g).to(dev) * sigma.view(-1, 1, 1, 1)
+    # oracle, fp32, on the device
+    dpo = {k: v.to(dev).requires_grad_(True) for k, v in dp.items()}
+    epo = {k: v.to(dev) for k, v in ep.items()}
+    _, emb_o = O.embedding_forward(epo, cfg["embedding"], sigma)
+    D_o = O.denoiser_forward(dpo, cfg["denoiser"], noisy, sigma, emb_o)
+    loss_o = O.training_loss(O.loss_weight(sigma, 0.5), D_o, clean)
+    loss_o.backward()
+    D_ref, loss_ref = D_o.detach(), loss_o.detach()
+    g_ref = {k: v.grad for k, v in dpo.items()}
+    del D_o, loss_o
+    torch.cuda.empty_cache()
+    # this library
+    _, e = emb_m(sigma)
+    D = den(noisy, sigma, e)
+    loss = T.fused_edm_loss(D, clean, sigma, 0.5)
+    loss.backward()
+    c_skip, c_out, _ = O.precond_coeffs(sigma, 0.5)
+    F_net, F_ref = (D.detach() - noisy * c_skip) / c_out, (D_ref - noisy * c_skip) / c_out     # the network branch alone
+    r_D, r_F, r_loss = rel(D, D_ref), rel(F_net, F_ref), rel(loss, loss_ref)
+    worst = ("", 0.0)
+    for k, p in den.named_parameters():
+        if p.ndim == 0:
+            continue
+        r = rel(p.grad, g_ref[k])
+        if r > worst[1]:
+            worst = (k, r)
+    print(f"B = 256 vs fp32 oracle on the GPU: D {r_D:.2e}, network branch {r_F:.2e}, loss {r_loss:.2e}, worst tensor gradient "
+          f"{worst[1]:.2e} ({worst[0]})")
+    assert r_D < 4e-2 and r_F < 4e-2 and r_loss < 4e-2
+    assert worst[1] < 6e-2, worst
