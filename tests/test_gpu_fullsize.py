@@ -113,29 +113,40 @@ def test_full_size_sampler_is_deterministic_and_graph_replay_matches_eager(dev):
     assert rel(half, eager[:64]) < 2e-2      # different tile shapes -> different bf16 summation order, not bit-identical
 
 
-def test_full_size_forward_backward_vs_fp32_oracle_on_the_gpu(dev):
-    """BASELINE.json's own training batch (256 x 3 x 32 x 32, the 35.6 M CIFAR net), element-wise: D, the loss and the
-    gradient of every parameter tensor against the fp32 oracle evaluated ON THE GPU with TF32 off (seconds instead of the
-    CPU's minutes). Eval mode / no dropout so that both sides see the same weights and masks; the bounds are the
-    accumulated-drift bounds of the small-batch config tests (tests/test_gpu_parity.py)."""
+@pytest.mark.parametrize("name,B", [("cifar", 256), ("mnist", 128), ("imagenet", 16)])
+def test_full_size_forward_backward_vs_fp32_oracle_on_the_gpu(dev, name, B):
+    """BASELINE.json's own training batches (CIFAR 256 x 3 x 32 x 32 on the 35.6 M net, MNIST 128 x 1 x 28 x 28 on the
+    87 M net; 16 latents of 4 x 64 x 64 on the 273 M ImageNet net — its micro-batch of 176 would need > 150 GB for the fp32
+    autograd graph), element-wise: D, the loss and the gradient of every parameter tensor against the fp32 oracle
+    evaluated ON THE GPU with TF32 off (seconds instead of the CPU's minutes). Eval mode / no dropout so that both sides
+    see the same weights and masks; the bounds are the accumulated-drift bounds of the small-batch config tests
+    (tests/test_gpu_parity.py)."""
+    import dataclasses
     import tinyedm_b200 as T
     from oracle import edm2_oracle as O
     from tests.helpers import build_modules, cifar_cfg, seeded_params
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    cfg = cifar_cfg(num_classes=None)
+    if name == "cifar":
+        cfg, img = cifar_cfg(num_classes=None), (3, 32, 32)
+    elif name == "mnist":
+        cfg, img = dict(O.MNIST), (1, 28, 28)
+        cfg["denoiser"] = dataclasses.replace(cfg["denoiser"], dropout_rate=0.0)
+    else:
+        cfg, img = dict(O.IMAGENET), (4, 64, 64)
     dp, ep, _ = seeded_params(cfg, seed=17)
     den, emb_m, _ = build_modules(cfg, dp, ep, None, dev)
     den.eval(); emb_m.eval()
-    B = 256
     g = torch.Generator().manual_seed(6)
-    clean = (0.5 * torch.randn(B, 3, 32, 32, generator=g)).clamp(-1, 1).to(dev)
+    clean = (0.5 * torch.randn(B, *img, generator=g)).clamp(-1, 1).to(dev)
     sigma = torch.exp(torch.randn(B, generator=g) * 1.2 - 1.2).to(dev)
-    noisy = clean + torch.randn(B, 3, 32, 32, generator=g).to(dev) * sigma.view(-1, 1, 1, 1)
+    noisy = clean + torch.randn(B, *img, generator=g).to(dev) * sigma.view(-1, 1, 1, 1)
+    ncls = cfg["embedding"].num_classes
+    labels = torch.randint(0, ncls, (B,), generator=g).to(dev) if ncls else None
     # oracle, fp32, on the device
     dpo = {k: v.to(dev).requires_grad_(True) for k, v in dp.items()}
     epo = {k: v.to(dev) for k, v in ep.items()}
-    _, emb_o = O.embedding_forward(epo, cfg["embedding"], sigma)
+    _, emb_o = O.embedding_forward(epo, cfg["embedding"], sigma, labels)
     D_o = O.denoiser_forward(dpo, cfg["denoiser"], noisy, sigma, emb_o)
     loss_o = O.training_loss(O.loss_weight(sigma, 0.5), D_o, clean)
     loss_o.backward()
@@ -144,7 +155,7 @@ def test_full_size_forward_backward_vs_fp32_oracle_on_the_gpu(dev):
     del D_o, loss_o
     torch.cuda.empty_cache()
     # this library
-    _, e = emb_m(sigma)
+    _, e = emb_m(sigma, labels)
     D = den(noisy, sigma, e)
     loss = T.fused_edm_loss(D, clean, sigma, 0.5)
     loss.backward()
@@ -158,7 +169,7 @@ def test_full_size_forward_backward_vs_fp32_oracle_on_the_gpu(dev):
         r = rel(p.grad, g_ref[k])
         if r > worst[1]:
             worst = (k, r)
-    print(f"B = 256 vs fp32 oracle on the GPU: D {r_D:.2e}, network branch {r_F:.2e}, loss {r_loss:.2e}, worst tensor gradient "
+    print(f"{name} B = {B} vs fp32 oracle on the GPU: D {r_D:.2e}, network branch {r_F:.2e}, loss {r_loss:.2e}, worst tensor gradient "
           f"{worst[1]:.2e} ({worst[0]})")
     assert r_D < 4e-2 and r_F < 4e-2 and r_loss < 4e-2
     assert worst[1] < 6e-2, worst
