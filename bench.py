@@ -31,6 +31,7 @@ METRIC = "CIFAR-10 EDM2 train img/s & 32-step Heun sample img/s at 1/2/4/8 B200"
 TRAIN_BATCH = 256
 SAMPLE_BATCH = 128
 SAMPLE_STEPS = 32
+EMA_GAMMA = 0.999                   # CPU arm's EMA decay (the value does not change the work: one lerp over every parameter)
 LR_RAMP = 1e-3                      # the schedule's ramp-up region (edm.py:306-317): keeps random-init training tame over the run
 # forward GFLOP per image (conv3x3 + conv1x1 + attention + linear), per-GPU batch, accumulation
 WORKLOADS = {
@@ -206,7 +207,9 @@ class CpuArm:
         sd = cfg["denoiser"].sigma_data
         if self.kind == "reference":
             den, emb = self.den.train(), self.emb.train()
-            opt = torch.optim.Adam(list(emb.parameters()) + list(den.parameters()), lr=0.02 * LR_RAMP, betas=(0.9, 0.999))
+            plist = list(emb.parameters()) + list(den.parameters())
+            opt = torch.optim.Adam(plist, lr=0.02 * LR_RAMP, betas=(0.9, 0.999))
+            ema = [q.detach().clone() for q in plist]          # EMAOptimizer's shadow copy (ema.py:270-284)
 
             def step():
                 noisy, sigma = O.diffuse(clean, torch.randn(batch), torch.randn_like(clean), cfg["P_mean"], cfg["P_std"])
@@ -216,11 +219,14 @@ class CpuArm:
                 opt.zero_grad(set_to_none=True)
                 loss.backward()
                 opt.step()
+                with torch.no_grad():
+                    torch._foreach_lerp_(ema, [q.detach() for q in plist], 1.0 - EMA_GAMMA)
                 return float(loss)
             return step
         dp, ep = self.dp, self.ep
         params = [v.requires_grad_(True) for v in dp.values()] + [v.requires_grad_(True) for k, v in ep.items() if k.endswith("weight")]
         opt = torch.optim.Adam(params, lr=0.02 * LR_RAMP, betas=(0.9, 0.999))
+        ema = [q.detach().clone() for q in params]
         weights = [v for k, v in list(dp.items()) + list(ep.items()) if k.endswith("weight")]
         p_drop = cfg["denoiser"].dropout_rate
         drop = (lambda t: torch.nn.functional.dropout(t, p_drop, True)) if p_drop > 0 else None
@@ -235,6 +241,8 @@ class CpuArm:
             opt.zero_grad(set_to_none=True)
             loss.backward()
             opt.step()
+            with torch.no_grad():
+                torch._foreach_lerp_(ema, [q.detach() for q in params], 1.0 - EMA_GAMMA)
             return float(loss)
         return step
 
@@ -263,6 +271,16 @@ class CpuArm:
             t0 = time.perf_counter()
             O.heun_solve(model, x0, labels, num_steps=heun_steps)
             return (time.perf_counter() - t0) / n_eval
+
+
+def workload_config(world: int, B: int) -> dict:
+    """`config` of the headline workload: the SAME dict on both arms (the reference arm times a bounded sample of it and
+    says which in `cpu_baseline.sample`); how each arm launches it is reported beside it, not inside."""
+    return {"workload": "CIFAR-10 35.6M unconditional EDM2 training step (cifar10.yaml): diffuse+embed+fwd+loss+bwd+"
+                        "allreduce+Adam+EMA", "per_gpu_batch": B, "global_batch": B * world, "image": "3x32x32",
+            "parallelism": f"dp{world}", "l2": "no explicit flush: each step streams >5 GB of activations (>> 126 MB L2)",
+            "weights": "random init, gain_out=1", "dropout": 0.13,
+            "lr": f"0.02 x {LR_RAMP} (the ramp-up region of the reference's schedule, edm.py:306-317; no work skipped)"}
 
 
 def cpu_kind_note(kind: str) -> str:
@@ -309,8 +327,8 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": v, "unit": "img/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "CIFAR-10 35.6M unconditional EDM2 training (cifar10.yaml) on the host CPU", "batch_per_step": batch,
-                   "lr": f"0.02 x {LR_RAMP} (ramp-up region of the schedule)"},
+        "config": workload_config(int(os.environ.get("WORLD_SIZE", max(1, args.gpus))), args.batch),
+        "sample_of_config": {"where": "host CPU, all threads", "batch_per_step": batch},
         "cpu_baseline": {"value": v, "unit": "img/s", "cores": threads, "kind": arm.kind, "sample": sample},
         "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "sampling": sampling, "configs": extra, "gpu_launches": 0}))
@@ -712,15 +730,9 @@ def run_b200(args) -> None:
             "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "CIFAR-10 35.6M unconditional EDM2 training step (cifar10.yaml): diffuse+embed+fwd+loss+bwd+"
-                                   "allreduce+fused Adam/EMA", "per_gpu_batch": B, "global_batch": B * world, "image": "3x32x32",
-                       "parallelism": f"dp{world}", "l2": "no explicit flush: each step streams >5 GB of activations (>> 126 MB L2)",
-                       "weights": "random init, gain_out=1", "dropout": 0.13,
-                       "lr": f"0.02 x {LR_RAMP} (the ramp-up region of the reference's schedule, edm.py:306-317; no work skipped)",
-                       "settle_steps": settle_steps,
-
-                       "launch": "CUDA graph replay of fwd+bwd (GraphedTrainStep) + 1 optimiser launch" if graph_mode
-                                 else "eager (one C-ABI call per kernel)"},
+            "config": workload_config(world, B),
+            "launch": {"mode": "CUDA graph replay of fwd+bwd (GraphedTrainStep) + 1 fused Adam/EMA launch" if graph_mode
+                       else "eager (one C-ABI call per kernel)", "settle_steps": settle_steps},
             "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": B * 3 * 32 * 32 * 4 + B * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "practical_bar": bar,
