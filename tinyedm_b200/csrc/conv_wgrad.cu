@@ -29,8 +29,8 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kBM = 128;      // Cout rows per CTA
 constexpr int kBN = 256;      // Cin columns per CTA (per tap)
-constexpr int kPrefRows = 64;  // preferred pixels per pipeline stage (4 stages of 48 KB)
-constexpr int kMaxRows = 128;  // fallback for widths where no <=64-row tile is a multiple of 16 (2 stages)
+constexpr int kPrefRows = 64;  // pixels per pipeline stage the shared-memory budget is sized for (4 stages of 48 KB)
+constexpr int kMaxRows = 128;  // largest pixel tile (then 2 stages in the single-CTA kernel); see wgrad_geometry
 constexpr int kMaxStages = 4;
 constexpr int kTileBytes = 4 * (kBM / 64 + kBN / 64) * kPrefRows * 128;  // 192 KB of operand stages
 constexpr int kSmemBytes = kTileBytes + 1024 /*align*/ + 1024 /*barriers*/;
@@ -191,25 +191,23 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
   }
 }
 
-// Pixel-tile geometry for the contraction: rows = NB*RH*W must be a multiple of 16 and <= 64.
-int wgrad_geometry_rows(int H, int W, int max_rows, int* RH, int* NB) {
+// Pixel-tile geometry for the contraction: rows = NB*RH*W (whole image rows, NB images when one image is smaller than
+// the tile) must be a multiple of 16 — one MMA contracts 16 pixels — and at most kMaxRows; the largest such tile wins
+// (fewer, longer pipeline stages measured faster than kPrefRows-sized ones on every shape of the three configs).
+// Widths with lcm(16, W) > kMaxRows (9, 13, 17, 18, ...) have no tile: the launchers refuse them, and the stand-alone
+// Conv2d module pads such maps with zero columns first (networks.py `_wgrad_width`).
+int wgrad_geometry(int H, int W, int* RH, int* NB) {
   int best = 0;
   for (int rh = 1; rh <= H; ++rh) {
     if (rh * W > kMaxRows) break;
-    int nb_max = kMaxRows / (rh * W);
+    const int nb_max = kMaxRows / (rh * W);
     for (int nb = 1; nb <= nb_max; ++nb) {
-      int rows = rh * W * nb;
+      const int rows = rh * W * nb;
       if (rows % 16 != 0) continue;
-      // prefer more rows; among equal, prefer fewer images per box (better halo reuse)
-      if (rows > best) { best = rows; *RH = rh; *NB = nb; }
+      if (rows > best) { best = rows; *RH = rh; *NB = nb; }   // among equal row counts: fewer images per box
     }
   }
-  return best;
-}
-
-int wgrad_geometry(int H, int W, int* RH, int* NB) {
-  if (wgrad_geometry_rows(H, W, kPrefRows, RH, NB) > 0) return 0;
-  return wgrad_geometry_rows(H, W, kMaxRows, RH, NB) > 0 ? 0 : -1;
+  return best > 0 ? 0 : -1;
 }
 
 

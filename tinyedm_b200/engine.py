@@ -404,7 +404,7 @@ class DenoiserEngine:
         """fp32 w_hat of every block's `embed` Linear, rows back to back: (sum C, E)."""
         first = self.embed_slots[0]
         E = first.cin
-        base = first.f32.storage_offset()
+        base = first.f32.storage_offset() - self.bank._f32_flat.storage_offset()
         return self.bank._f32_flat[base:base + self.n_mod * E].view(self.n_mod, E)
 
     # =====================================================================================================
@@ -692,7 +692,8 @@ class DenoiserEngine:
             g_emb = torch.empty((B, E), device=emb.device, dtype=F32)
             ops.sgemm(d_lin, self.w_embed_all, g_emb, B, E, N, N, E, E, False, False)
         first = self.embed_slots[0]
-        gh_all = self.bank._ghat_flat[first.ghat.storage_offset():first.ghat.storage_offset() + N * E].view(N, E)
+        base = first.ghat.storage_offset() - self.bank._ghat_flat.storage_offset()
+        gh_all = self.bank._ghat_flat[base:base + N * E].view(N, E)
         ops.sgemm(d_lin, emb, gh_all, N, E, B, N, E, E, True, False, 1.0, 1.0)   # += : g_hat was zeroed by the memset
         return g_emb
 

@@ -115,9 +115,10 @@ class Conv2d(nn.Module):
         slot = bank.slots[0]
         k, ci, co = self.kernel_size, self.in_channels, self.out_channels
         gh = gy.permute(0, 2, 3, 1).to(BF16)
+        Wp = _wgrad_width(gh.shape[2])
         if pad is None:
             gh = gh.contiguous()
-            ops.conv2d_wgrad(gh, xh, slot.ghat, k)
+            ops.conv2d_wgrad(_pad_width(gh, Wp), _pad_width(xh, Wp), slot.ghat, k)
             bank.backward()
             gx = None
             if need_gx:
@@ -127,7 +128,7 @@ class Conv2d(nn.Module):
         gp = torch.zeros(gh.shape[:3] + (cop,), device=gy.device, dtype=BF16)
         gp[..., :co] = gh
         dw = torch.zeros((cop, k * k, cip), device=gy.device, dtype=F32)
-        ops.conv2d_wgrad(gp, xh, dw, k)
+        ops.conv2d_wgrad(_pad_width(gp, Wp), _pad_width(xh, Wp), dw, k)
         # dL/dw_hat back in parameter layout (Cout, Cin, k, k) for the weight-norm Jacobian
         slot.ghat.copy_(dw.view(cop, k, k, cip)[:co, :, :, :ci].permute(0, 3, 1, 2).reshape(co, ci * k * k))
         bank.backward()
@@ -143,6 +144,26 @@ class Conv2d(nn.Module):
 
     def extra_repr(self) -> str:
         return f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}"
+
+
+def _wgrad_width(W: int) -> int:
+    """Smallest width >= W the weight-gradient kernels can tile: their pixel tiles are whole rows, a multiple of 16 pixels
+    and at most 128 (csrc/conv_wgrad.cu `wgrad_geometry`), i.e. lcm(16, W') <= 128. Every feature map of the three
+    configs qualifies as it is (64, 32, 16, 8, 28, 14, 7); 9, 13, 17, 18 ... do not."""
+    w = W
+    while w < 128 and math.lcm(16, w) > 128:
+        w += 1
+    return w
+
+
+def _pad_width(t: Tensor, Wp: int) -> Tensor:
+    """(B, H, W, C) -> (B, H, Wp, C) with zero columns on the right. Exact for the weight gradient: the new output-gradient
+    columns are zero, and the new input columns are the zeros the convolution's own padding already stands for."""
+    if t.shape[2] == Wp:
+        return t
+    out = torch.zeros((t.shape[0], t.shape[1], Wp, t.shape[3]), device=t.device, dtype=t.dtype)
+    out[:, :, :t.shape[2]] = t
+    return out
 
 
 class _LinearFn(torch.autograd.Function):
