@@ -206,3 +206,38 @@ def test_standalone_kernels_write_only_inside_their_buffers(dev):
         bad = g.violations()
     assert len(g.tracked) > 40
     assert bad == [], "\n".join(bad[:20])
+
+
+@pytest.mark.parametrize("name,B", [("cifar", 256), ("mnist", 128), ("imagenet", 16)])
+def test_full_size_steps_write_only_inside_their_buffers(dev, name, B, monkeypatch):
+    """The three real architectures at their own feature-map sizes and (CIFAR, MNIST) batch sizes: one training step with
+    dropout and the optimiser, one eval forward, under the guard."""
+    from tinyedm_b200 import configs
+    monkeypatch.setenv("TEDM_CUDA_GRAPHS", "0")
+    cfg = {"cifar": configs.CIFAR10, "mnist": configs.MNIST, "imagenet": configs.IMAGENET}[name]
+    C, H, W = {"cifar": (3, 32, 32), "mnist": (1, 28, 28), "imagenet": (4, 64, 64)}[name]
+    torch.manual_seed(11)
+    clean = (0.5 * torch.randn(B, C, H, W, device=dev)).clamp(-1, 1)
+    with GuardedAllocs() as g:
+        model = configs.build_edm(cfg).to(dev)
+        ncls = model.embedding.num_classes
+        ncls = ncls if ncls and ncls > 0 else None
+        labels = torch.randint(0, ncls, (B,), device=dev) if ncls else torch.zeros(B, dtype=torch.long, device=dev)
+        with torch.no_grad():
+            model.denoiser.gain_out.fill_(1.0)
+        opt = model.configure_optimizers()["optimizer"]
+        model.train()
+        loss = model.training_step((clean, labels), 0)
+        loss.backward()
+        opt.step()
+        model.eval()
+        with torch.no_grad():
+            D = model(clean, torch.rand(B, 1, 1, 1, device=dev) + 0.2, labels if ncls else None)
+        assert torch.isfinite(loss) and torch.isfinite(D).all()
+        bad = g.violations()
+        n = len(g.tracked)
+        del model, opt, loss, D
+    g.tracked.clear()
+    torch.cuda.empty_cache()
+    assert n > 300, n
+    assert bad == [], "\n".join(bad[:20])
