@@ -4,11 +4,12 @@ identical launches.
 
 * Forward: every kernel is deterministic by construction (no atomics on the forward path), so eight evaluations of the same
   (noisy, sigma, labels) must be BIT-identical, for each of the three architectures at its own batch size.
-* Backward: not bit-repeatable by design — split-K weight-gradient partials meet in fp32 reduce-adds, the modulation /
-  gain / attention dK,dV reductions use fp32 atomics, and an fp32 sum that lands on the other side of a bf16 rounding
-  boundary flips one ulp of an activation gradient, which the rest of the backward chain then carries along: the noise
-  GROWS towards the first encoder blocks (the end of the chain) and stays orders below what a race would do (O(1) in a
-  tile). Measured on one B200 over 3 repeats (the test prints it), CIFAR B = 256 / MNIST B = 128 / ImageNet-latent
+* Backward: not bit-repeatable by design — split-K weight-gradient partials meet in fp32 TMA reduce-adds and the
+  per-image modulation / ScaleLong-gain reductions in fp32 atomics (attention has none). The gain gradient re-enters the
+  activation-gradient chain through the skip tensors: an fp32 sum that lands on the other side of a bf16 rounding boundary
+  flips one ulp of an activation gradient (a relative perturbation d before rounding becomes ~sqrt(d * 2^-8) after it),
+  which the rest of the chain carries along, so the noise GROWS towards the first encoder blocks (the end of the chain)
+  while staying orders below what a race would do (O(1) in a tile). Measured on one B200 over 3 repeats (the test prints it), CIFAR B = 256 / MNIST B = 128 / ImageNet-latent
   B = 16: embedding gradient 1.0e-4 / 2.1e-4 / 1.7e-4; worst parameter tensor 4.5e-5 / 2.0e-4 / 3.5e-4 (always
   `encoder_blocks.{0,1}.conv_3x3_1.weight`); worst 0-d block gain (one number summing a whole layer) 8.6e-5 / 1.1e-3 /
   1.1e-3. Bounds: 2e-3 relative L2 for tensors, 2e-2 for the scalars — 5x below the bf16 parity bound those gradients are
