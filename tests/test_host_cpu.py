@@ -177,3 +177,20 @@ def test_edm_module_surface():
     cfgd = m.configure_optimizers()
     assert isinstance(cfgd["optimizer"], T.FusedAdamEMA) and cfgd["lr_scheduler"]["interval"] == "epoch"
     assert cfgd["optimizer"].param_groups[0]["lr"] == pytest.approx(0.02 * 1e-8)   # LambdaLR applied factor(0)
+
+
+def test_wgrad_width_padding_rule_matches_the_kernel_geometry():
+    """networks.py `_wgrad_width` (stand-alone Conv2d) against the rule of csrc/conv_wgrad.cu `wgrad_geometry`: a pixel tile is
+    rh whole rows of nb images, rh * W * nb a multiple of 16 and at most 128."""
+    from tinyedm_b200.networks import _wgrad_width
+
+    def tileable(H, W):
+        return any((rh * W * nb) % 16 == 0 for rh in range(1, H + 1) for nb in range(1, 128 // (rh * W) + 1) if rh * W <= 128)
+
+    for W in range(1, 129):
+        Wp = _wgrad_width(W)
+        assert W <= Wp <= 128 and tileable(1, Wp) and tileable(Wp, Wp)
+        assert Wp == W or not tileable(W, W)                       # pads only what the kernel cannot tile ...
+        assert all(not tileable(w, w) for w in range(W, Wp))       # ... and by as little as possible
+    for W in (64, 32, 16, 8, 28, 14, 7):                           # every feature map of the three configs runs unpadded
+        assert _wgrad_width(W) == W
