@@ -110,8 +110,7 @@ def _worker(rank, world, port, out, backend="nccl"):
 def test_data_parallel_gradients_match_single_process_two_ranks_on_one_gpu():
     """world size 2 over gloo with both ranks on cuda:0: the same engine / bucket / no_sync / finish_backward code as under
     NCCL, runnable where only one GPU is visible."""
-    if not torch.cuda.is_available():
-        pytest.skip("needs a CUDA device")
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device (they fail, not skip, without one)"
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()

@@ -15,8 +15,7 @@ BF = torch.bfloat16
 
 @pytest.fixture(scope="module")
 def dev():
-    if not torch.cuda.is_available():
-        pytest.skip("needs a CUDA device")
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device (they fail, not skip, without one)"
     return torch.device("cuda:0")
 
 
