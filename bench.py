@@ -616,6 +616,12 @@ def run_b200(args) -> None:
     ms_e2e = timed(e2e_step, args.steps)
     clk = clocks.summarise(c0, max(c1, c0 + 1))
     final_loss = float(loss_host[args.steps - 1])
+    if os.environ.get("TEDM_BENCH_DIAG") == "1" and rank == 0:
+        # diagnosis only (stderr): the same two windows again, to tell an ordering effect from a difference of the input paths
+        again = [(n, timed(f, args.steps) / args.steps) for n, f in
+                 (("device", lambda i: run_step((dev_imgs[i % n_pool], dev_lbls[i % n_pool]))), ("host", e2e_step)) * 2]
+        print(f"bench.py diag: ms/step device {ms_dev / args.steps:.3f}, host {ms_e2e / args.steps:.3f}, then "
+              + ", ".join(f"{n} {t:.3f}" for n, t in again), file=sys.stderr)
     value = world * B * args.steps / (ms_dev / 1e3)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
 
